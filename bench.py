@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py — RK4 sample-steps/sec of the closed-loop rollout (BASELINE.json metric) on N B200s of one box.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload swap12|singlequad|swarm50|...] [--impl reference]
+
+A "step" is one OCflow call (mean mode) over one batch of synthetic initial states drawn from the problem's
+initial distribution; the default workload is BASELINE.json configs[1]: the swap12 pretrained
+checkpoint, nt = 50, 2^20 samples per GPU, fp32.  Under torchrun (N > 1) every rank rolls out its own shard
+(weak scaling: per-GPU work fixed) and the step ends with the single all-reduce of the 8-double cost vector.
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = the same metric through the public
+API with host (pinned) buffers, copies inside the timed region; `roofline` = algorithmic FLOP/s of the rollout
+kernel against the FP32 (or FP64) FMA peak measured live on the same device; `cpu_baseline` = the CPU oracle port
+(torch CPU, all host threads) timed on a bounded sample of the same workload.
+`--impl reference` times only that CPU arm (the reference is pure Python/torch and cannot travel to the GPU box;
+oracle/ocflow_oracle.py is its restatement, pinned against the reference's outputs in tests/).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import numpy as np   # noqa: E402
+import torch         # noqa: E402
+
+# per-GPU samples, nt, dtype, CPU-sample size; flops/sample-step = 4 (4 m D + 4 m^2 (nTh-1) + min(2 D^2, 4 r D))
+WORKLOADS = {
+    "softcorridor": dict(ckpt="softcorridor", n=1 << 20, nt=50, dtype="f32", n_cpu=65536),
+    "swap2": dict(ckpt="swap2", n=1 << 20, nt=50, dtype="f32", n_cpu=65536),
+    "swap12": dict(ckpt="swap12", n=1 << 20, nt=50, dtype="f32", n_cpu=65536),
+    "singlequad": dict(ckpt="singlequad", n=1 << 22, nt=50, dtype="f32", n_cpu=32768),
+    "swarm50": dict(ckpt="swarm50", n=1 << 24, nt=80, dtype="f32", n_cpu=2048),
+    "config5": dict(ckpt=None, n=1 << 20, nt=50, dtype="f64", n_cpu=1024),
+}
+
+
+def flops_per_sample_step(d, m, nTh, r):
+    D = d + 1
+    return 4 * (4 * m * D + 4 * m * m * (nTh - 1) + min(2 * D * D, 4 * r * D))
+
+
+def build_case(workload, device, dtype):
+    """-> net, prob, xInit (on device), meta, var0 — from committed fixtures only (no /root/reference)."""
+    import neuraloc_b200 as nb
+    from helpers import load_ckpt
+    w = WORKLOADS[workload]
+    cvt = lambda v: v.to(dtype).to(device)
+    if w["ckpt"] is None:       # BASELINE.json configs[4]: random-init swarm50-shape Phi
+        alph = [1800.0, 1e7, 25000.0, 2.0, 1.0, 3.0]
+        torch.manual_seed(0)
+        net = nb.Phi(nTh=2, m=512, d=150, alph=alph)
+        meta = dict(data="swarm50", alph=alph, var0=0.1, m=512, nTh=2)
+    else:
+        sd, meta = load_ckpt(w["ckpt"])
+        net = None
+    prob, x0, _, xinit = nb.initProb(meta["data"], 2, 2, var0=1.0, alph=meta["alph"], cvt=cvt)
+    prob.eval()
+    if net is None:
+        net = nb.Phi(nTh=meta["nTh"], m=meta["m"], d=x0.shape[1], alph=meta["alph"])
+        net.load_state_dict(sd)
+    net = net.to(dtype).to(device)
+    net.eval()
+    return net, prob, xinit, meta
+
+
+def sample_x(workload, xinit, var0, n, seed, device, dtype):
+    """x ~ rho_0 of the problem: xInit + var0 N(0,I); singlequad perturbs the position only."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    d = xinit.shape[1]
+    if workload == "singlequad":
+        x = torch.zeros(n, d, device=device, dtype=dtype)
+        x[:, :3] = -1.5 + var0 * torch.randn(n, 3, generator=g, device=device, dtype=dtype)
+        return x
+    x = torch.randn(n, d, generator=g, device=device, dtype=dtype)
+    x.mul_(var0).add_(xinit.to(device))
+    return x
+
+
+def cpu_rate(workload, n_cpu, nt, dtype, threads):
+    """sample-steps/s of the CPU oracle port on a bounded sample (one small warm-up call, one timed call)."""
+    from oracle import ocflow_oracle as orc
+    from helpers import load_ckpt
+    w = WORKLOADS[workload]
+    torch.set_num_threads(threads)
+    if w["ckpt"] is None:
+        import neuraloc_b200 as nb
+        alph = [1800.0, 1e7, 25000.0, 2.0, 1.0, 3.0]
+        torch.manual_seed(0)
+        sd = nb.Phi(nTh=2, m=512, d=150, alph=alph).state_dict()
+        meta = dict(data="swarm50", alph=alph, var0=0.1)
+    else:
+        sd, meta = load_ckpt(w["ckpt"])
+    P = orc.params_from_state_dict(sd, dtype)
+    D, xinit = orc.make_problem(meta["data"], meta["alph"], dtype)
+    x = sample_x(workload, xinit, meta["var0"], n_cpu, 1234, "cpu", dtype)
+    with torch.no_grad():
+        orc.ocflow(x[: max(1, n_cpu // 16)], P, D, [0.0, 1.0], nt, "rk4", meta["alph"])
+        t0 = time.perf_counter()
+        orc.ocflow(x, P, D, [0.0, 1.0], nt, "rk4", meta["alph"])
+        dt = time.perf_counter() - t0
+    return n_cpu * nt / dt, dt
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons of one GPU while the timed region runs (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.thread = [], None, None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t_begin, t_end):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        for t, line in self.rows:
+            f = [v.strip() for v in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mx = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            smax = mx
+            if t_begin - 0.05 <= t <= t_end + 0.05:
+                sm.append(clk)
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:       # region shorter than the sampling period: use whatever was seen
+            sm = [float(l.split(",")[0]) for _, l in self.rows if l and l.split(",")[0].strip().replace(".", "").isdigit()]
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="swap12", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    W = WORKLOADS[args.workload]
+    n = args.n or W["n"]
+    nt = W["nt"]
+    dtype = torch.float32 if W["dtype"] == "f32" else torch.float64
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    threads = os.cpu_count() or 1
+
+    # ------------------------------------------------------------------ reference arm: CPU oracle port on host cores
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        rates = []
+        for _ in range(max(1, args.steps)):
+            r, dt = cpu_rate(args.workload, W["n_cpu"], nt, dtype, threads)
+            rates.append((r, dt))
+        rate = W["n_cpu"] * nt * len(rates) / sum(dt for _, dt in rates)
+        sample = "%d samples x nt=%d per step (of %d), torch CPU %s, %d threads" % (W["n_cpu"], nt, n, torch.__version__, threads)
+        line = {"impl": "reference", "metric": "rk4_sample_steps_per_sec", "value": rate, "unit": "sample-steps/s",
+                "n_gpus": args.gpus, "steps": len(rates), "warmup": 1, "ms_per_step": 1e3 * sum(dt for _, dt in rates) / len(rates),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
+                "config": {"workload": "%s pretrained checkpoint, nt=%d, x ~ xInit + var0*N(0,I)" % (args.workload, nt),
+                           "samples_per_step": W["n_cpu"]},
+                "cpu_baseline": {"value": rate, "unit": "sample-steps/s", "cores": threads, "kind": "port", "sample": sample},
+                "e2e": {"value": rate, "unit": "sample-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm
+    import neuraloc_b200 as nb
+    lib = nb._cabi.lib()      # raises if the CUDA library is missing: no fallback
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=device)
+
+    net, prob, xinit, meta = build_case(args.workload, device, dtype)
+    d = xinit.shape[1]
+    x = sample_x(args.workload, xinit, meta["var0"], n, 1234 + rank, device, dtype)
+    alph = meta["alph"]
+    fl = flops_per_sample_step(d, meta["m"], meta["nTh"], min(10, d + 1))
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=device)      # > L2 (126 MB)
+
+    def step():
+        sums = nb.ocflow_sums(x, net, prob, [0.0, 1.0], nt, "rk4", alph)
+        if dist is not None:
+            dist.all_reduce(sums)
+        return sums
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            sums = step()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        sampler = ClockSampler(local_rank) if rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+        l0 = nb._cabi.launch_count()
+        t_begin = time.perf_counter()
+        for e0, e1 in ev:
+            flush.zero_()                 # L2 flush between timed iterations (not timed)
+            e0.record()
+            sums = step()
+            e1.record()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        t_end = time.perf_counter()
+        launches = nb._cabi.launch_count() - l0
+        clocks = sampler.stop(t_begin, t_end) if sampler else None
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in ev]
+    tot_ms = torch.tensor([sum(step_ms)], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(tot_ms, op=dist.ReduceOp.MAX)
+    tot_s = float(tot_ms) * 1e-3
+    value = world * n * nt * args.steps / tot_s
+    Jc, cs = nb.costs_from_sums(sums, alph, dtype)
+
+    # ---- e2e: public API with HOST buffers (H2D of the step's inputs + D2H of its result inside the timed region)
+    xh = x.cpu().pin_memory()
+    with torch.no_grad():
+        for _ in range(max(1, min(2, args.warmup))):
+            nb.ocflow_sums(xh, net, prob, [0.0, 1.0], nt, "rk4", alph)
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            sh = nb.ocflow_sums(xh, net, prob, [0.0, 1.0], nt, "rk4", alph)     # noc_ocflow_host: H2D + rollout + D2H + sync
+            if dist is not None:
+                sd_ = sh.to(device)
+                dist.all_reduce(sd_)
+                sh = sd_.cpu()
+        torch.cuda.synchronize()
+        e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if dist is not None:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_val = world * n * nt * args.steps / float(e2e_s)
+    e2e_Jc = float(nb.costs_from_sums(sh, alph, dtype)[0])
+
+    if rank == 0:
+        pk = __import__("ctypes").c_double(0.0)
+        nb._cabi.check(lib.noc_measure_fma_peak(0 if W["dtype"] == "f32" else 1, pk))
+        peak = pk.value
+        ach = n * nt * fl / (statistics.mean(step_ms) * 1e-3) / 1e12        # per GPU: the rollout kernel of one launch
+        line = {
+            "metric": "rk4_sample_steps_per_sec", "value": value, "unit": "sample-steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(tot_ms) / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": W["dtype"], "data": "synthetic",
+            "config": {"workload": "%s %s, nt=%d, %d samples per GPU, x ~ xInit + var0*N(0,I) seed 1234+rank, eval mode"
+                                   % (args.workload, "pretrained checkpoint" if W["ckpt"] else "random-init swarm50-shape Phi", nt, n),
+                       "samples_per_gpu": n, "nt": nt, "d": d, "m": meta["m"], "nTh": meta["nTh"], "parallelism": "dp%d (row shards, one all-reduce of 8 doubles)" % world,
+                       "l2": "flushed between timed steps (256 MiB write, untimed)", "flops_per_sample_step": fl,
+                       "Jc": float(Jc), "Jc_e2e": e2e_Jc},
+            "clocks": clocks,
+            "e2e": {"value": e2e_val, "unit": "sample-steps/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
+                    "d2h_bytes_per_step": 64},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "achieved": ach, "peak": peak,
+                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "peak_source": "measured live: register-resident FMA micro-benchmark on all SMs (noc_measure_fma_peak); "
+                                        "MEASURED_PEAKS.json has no FP32/FP64 FMA figure"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r, dt = cpu_rate(args.workload, W["n_cpu"], nt, dtype, threads)
+            line["cpu_baseline"] = {"value": r, "unit": "sample-steps/s", "cores": threads, "kind": "port",
+                                    "sample": "%d of the %d samples, nt=%d, one call, %.1f s; torch CPU %s oracle port (the Python reference cannot travel)"
+                                              % (W["n_cpu"], n, nt, dt, torch.__version__)}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

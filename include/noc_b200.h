@@ -1,0 +1,151 @@
+/*
+ * noc_b200.h — C ABI of the B200-native NeuralOC rollout library (libnoc_b200.so).
+ *
+ * The reference (donken/NeuralOC) is pure Python on PyTorch and has NO FFI; the drop-in boundary
+ * for its hot path is the Python function
+ *
+ *     OCflow(x, Phi, prob, tspan, nt, stepper="rk4", alph=[1.0]*6, intermediates=False, noMean=False)
+ *                                                                        -- src/OCflow.py:7
+ *
+ * plus the duck-typed Phi (src/Phi.py:56-138) and problem objects (src/problem/*.py) it receives.
+ * Each entry point below names the reference interface it replaces.  A maintainer binds these
+ * with ctypes; neuraloc_b200/_cabi.py is exactly that binding.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / C++ types cross this boundary
+ *   - every function returns NOC_OK (0) or a negative noc_status; the message of the last error
+ *     of the calling thread is available from noc_last_error(); nothing ever calls exit()
+ *   - "dev" pointers are CUDA device pointers on the current device, "host" pointers are host
+ *     memory (pinned or pageable); `stream` is a cudaStream_t passed as void* (NULL = default stream)
+ *   - dtype: NOC_F32 or NOC_F64 selects the arithmetic type of x, of all Phi / problem tensors and
+ *     of the per-sample / trajectory outputs (the reference's --prec single|double)
+ *   - all matrices are row-major and contiguous, in the reference's own checkpoint layout
+ *     (src/Phi.py:77-87, 32-36): no re-layout is required of the caller
+ *   - re-entrant and stream-ordered: work is enqueued on `stream`; only the *_host variants and
+ *     noc_measure_* synchronise
+ *   - there is no CPU implementation behind any of these: without a CUDA device they fail with
+ *     NOC_ERR_CUDA
+ */
+#ifndef NOC_B200_H
+#define NOC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NOC_ABI_VERSION 1
+
+typedef enum noc_status {
+    NOC_OK = 0,
+    NOC_ERR_ARG = -1,          /* invalid argument (null pointer, negative size, bad enum) */
+    NOC_ERR_UNSUPPORTED = -2,  /* valid in the reference but not instantiated here (message says what) */
+    NOC_ERR_CUDA = -3,         /* a CUDA runtime call failed / no device */
+    NOC_ERR_NOMEM = -4         /* shared-memory or device-memory budget exceeded */
+} noc_status;
+
+enum { NOC_F32 = 0, NOC_F64 = 1 };
+
+/* problem classes: src/problem/Cross2D.py, SwarmTraj.py, Quadcopter.py */
+enum { NOC_PROB_CROSS2D = 0, NOC_PROB_SWARMTRAJ = 1, NOC_PROB_QUADCOPTER = 2 };
+/* prob.obstacle strings: None, 'softcorridor', 'hardcorridor' (Cross2D.py:43-52), 'blocks' (SwarmTraj.py:47-51) */
+enum { NOC_OBS_NONE = 0, NOC_OBS_SOFTCORRIDOR = 1, NOC_OBS_HARDCORRIDOR = 2, NOC_OBS_BLOCKS = 3 };
+/* stepper: 'rk4' (OCflow.py:157-184), 'rk1' (:143-155); any other string integrates nothing (:46-49) */
+enum { NOC_STEP_NONE = 0, NOC_STEP_RK1 = 1, NOC_STEP_RK4 = 4 };
+/* return modes of OCflow: default means (:80-95), noMean=True (:66-76), intermediates=True (:37-55,92-93) */
+enum { NOC_MODE_MEAN = 0, NOC_MODE_NOMEAN = 1, NOC_MODE_INTERMEDIATES = 2 };
+
+/* The value network Phi(s) = w'N(s) + 0.5 s'A'A s + c_w's + c_b, s = [x, t]   (src/Phi.py:56-96).
+ * Replaces reading `Phi.A, Phi.c, Phi.w, Phi.N.layers[i]` of the live nn.Module. */
+typedef struct noc_phi_t {
+    int32_t d;        /* space dimension; the net input is D = d + 1                              */
+    int32_t m;        /* hidden width                                                               */
+    int32_t nTh;      /* number of ResNet layers, >= 2 (Phi.py:25-27)                               */
+    int32_t r;        /* rows of A = min(10, d+1) (Phi.py:75)                                       */
+    double h;         /* ResNet step N.h = 1/(nTh-1) (Phi.py:38); <= 0 means "use 1/(nTh-1)"        */
+    const void* A;    /* dev [r, D]          state_dict key "A"                                     */
+    const void* c_w;  /* dev [1, D]          "c.weight"                                             */
+    const void* c_b;  /* dev [1]             "c.bias"                                               */
+    const void* w;    /* dev [1, m]          "w.weight"                                             */
+    const void* const* K;  /* HOST array of nTh dev pointers: K[0] [m, D] "N.layers.0.weight", K[i] [m, m] */
+    const void* const* b;  /* HOST array of nTh dev pointers: b[i] [m]    "N.layers.i.bias"        */
+} noc_phi_t;
+
+/* The duck-typed problem object (attributes read by OCflow through calcLHQW / calcGradpH / calcCtrls /
+ * xtarget: Cross2D.py:30-52, SwarmTraj.py:36-51, Quadcopter.py:37-48). */
+typedef struct noc_prob_t {
+    int32_t kind;       /* NOC_PROB_*                                                               */
+    int32_t obstacle;   /* NOC_OBS_*                                                                */
+    int32_t training;   /* prob.training: 0 after prob.eval(), 1 after prob.train()                 */
+    int32_t nAgents;
+    int32_t agentDim;   /* 2 (Cross2D), 3 (SwarmTraj), 12 (Quadcopter)                              */
+    double alph_Q, alph_W, r;
+    double mass, grav;  /* Quadcopter only (Quadcopter.py:37)                                       */
+    const void* xtarget; /* dev [d], dtype-typed                                                    */
+} noc_prob_t;
+
+int noc_version(void);                 /* NOC_ABI_VERSION of the loaded library */
+const char* noc_last_error(void);      /* thread-local, never NULL */
+
+/* Device facts used by the host side (bench / tests): SM count, compute capability, shared memory per block. */
+int noc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes);
+
+/* Number of control channels calcCtrls returns for this problem: d (Cross2D.py:164, SwarmTraj.py:166)
+ * or 4 * nAgents (Quadcopter.py:165-174). Negative on error. */
+int noc_ctrl_dim(const noc_prob_t* prob, int32_t d);
+
+/* Fill `table` (HOST, nt * 5 doubles) with, per step k: t_a, t_a + h'/2, t_a + h', t_ctrl, h' where the values
+ * replay the reference's double arithmetic `tk += h`, `h' = (tk + h) - tk` (OCflow.py:25,35,47,50,53,169). */
+int noc_stage_times(double t0, double t1, int32_t nt, double* table);
+
+/*
+ * noc_ocflow — replaces OCflow(x, Phi, prob, tspan, nt, stepper, alph, intermediates, noMean), src/OCflow.py:7-95,
+ * i.e. stepRK4/stepRK1 (:143-184), ocOdefun (:104-140), Phi.getGrad / Phi.forward (Phi.py:91-138) and
+ * prob.calcLHQW / calcGradpH / calcCtrls, as ONE persistent kernel launch (+ a 1-block finishing reduction).
+ *
+ *   x            dev [n, d]
+ *   stage_times  HOST [nt * 5] from noc_stage_times(), or NULL to have it computed from (t0, t1, nt)
+ *   alph         HOST [6]; only alph[0], [3], [4], [5] are used (quirk 7: Q/W weights live in prob)
+ *   mode == NOC_MODE_MEAN:          out_costs dev [8] DOUBLE = sums over the n samples of
+ *                                   [L, G, HJt, HJfin, HJgrad, Q, W] followed by the sample count n
+ *                                   (divide by the count for the reference's means; sums so that shards add)
+ *   mode == NOC_MODE_NOMEAN:        out_costs dev [n, 8] dtype-typed rows [Jc, L, G, HJt, HJfin, HJgrad, Q, W]
+ *   mode == NOC_MODE_INTERMEDIATES: zFull dev [n, d+4, nt+1], ctrlFull dev [n, nCtrl, nt+1] (last dim contiguous),
+ *                                   out_costs may be NULL
+ */
+int noc_ocflow(const noc_phi_t* phi, const noc_prob_t* prob, const void* x, int64_t n,
+               const double* stage_times, double t0, double t1, int32_t nt, int32_t stepper,
+               const double* alph, int32_t mode, int32_t dtype,
+               void* out_costs, void* zFull, void* ctrlFull, void* stream);
+
+/* Same call with HOST buffers for x and for every output (what evalOC.py / timeOC.py pass: CPU tensors).
+ * Copies x host->device, runs noc_ocflow on `stream`, copies the results back and synchronises `stream`.
+ * phi / prob tensors stay device pointers (uploaded once by the caller). */
+int noc_ocflow_host(const noc_phi_t* phi, const noc_prob_t* prob, const void* x_host, int64_t n,
+                    const double* stage_times, double t0, double t1, int32_t nt, int32_t stepper,
+                    const double* alph, int32_t mode, int32_t dtype,
+                    void* out_costs_host, void* zFull_host, void* ctrlFull_host, void* stream);
+
+/* noc_phi_eval — replaces Phi.forward (Phi.py:91-96) and Phi.getGrad (Phi.py:99-138) on a batch.
+ *   s dev [n, d+1]; out_phi dev [n] or NULL; out_grad dev [n, d+1] or NULL. */
+int noc_phi_eval(const noc_phi_t* phi, const void* s, int64_t n, int32_t dtype,
+                 void* out_phi, void* out_grad, void* stream);
+
+/* noc_prob_eval — replaces prob.calcLHQW(x,p), prob.calcGradpH(x,p), prob.calcCtrls(x,p) on a batch.
+ *   x, p dev [n, d]; out_lhqw dev [n, 4] = (L, H, Q, W); out_gradpH dev [n, d]; out_ctrls dev [n, nCtrl];
+ *   any output may be NULL. */
+int noc_prob_eval(const noc_prob_t* prob, const void* x, const void* p, int64_t n, int32_t d, int32_t dtype,
+                  void* out_lhqw, void* out_gradpH, void* out_ctrls, void* stream);
+
+/* Roofline denominators measured on the device the library runs on: a register-resident
+ * FMA micro-benchmark on all SMs. Returns TFLOP/s (2 flops per FMA) in *tflops. Synchronises. */
+int noc_measure_fma_peak(int32_t dtype, double* tflops);
+
+/* Kernel-launch counter (number of CUDA kernels this library launched in this process); bench.py reports it. */
+int64_t noc_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NOC_B200_H */

@@ -1,0 +1,501 @@
+// noc_api.cu — C ABI (include/noc_b200.h) over the persistent rollout kernel.
+//
+// Host-side work per call: pick a tile configuration for (dtype, m, D), lay out the shared-memory
+// panels, pack the value-network weights into the K-major permuted blob the kernel reads (a tiny
+// kernel, stream-ordered), launch ONE rollout kernel + a 1-block finishing reduction.  All scratch is
+// stream-ordered (cudaMallocAsync), so calls on different streams do not interfere.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "noc_launch.cuh"
+
+namespace noc {
+
+static thread_local std::string g_err;
+static std::atomic<long long> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+void count_launch() { g_launches++; }
+
+// out[q] = sum over CTAs of partials[cta][q], fixed order (deterministic); out[7] = sample count
+static __global__ void finish_costs_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+    int q = threadIdx.x;
+    if (q < 8) {
+        double s = 0.0;
+        for (int b = 0; b < nblocks; ++b) s += partials[b * 8 + q];
+        out[q] = s;
+    }
+}
+
+int launch_finish(const double* partials, int nblocks, double* out, cudaStream_t st) {
+    finish_costs_kernel<<<1, 32, 0, st>>>(partials, nblocks, out);
+    count_launch();
+    NOC_CUDA(cudaGetLastError());
+    return NOC_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FMA peak micro-benchmark (roofline denominator)
+// ------------------------------------------------------------------------------------------------
+template <typename real>
+static __global__ void __launch_bounds__(256) fma_peak_kernel(real* out, int iters, real a, real b) {
+    real acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = real(threadIdx.x + i);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = r_fma(acc[i], a, b);
+    }
+    real s = real(0);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i];
+    if (s == real(123456789)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the loop alive
+}
+
+struct CfgInfo {
+    int id, PB, TS, TSP, NT, TPS, NWOxWO;
+    bool wsmem;
+    size_t elt;
+    const char* name;
+};
+template <class C>
+static CfgInfo info_of(int id, const char* name) {
+    return CfgInfo{id, C::PB, C::TS, C::TSP, C::NT, C::TPS, C::NWO * C::WO, C::WSMEM, sizeof(typename C::real), name};
+}
+static const CfgInfo kCfgs[] = {
+    info_of<CfgF_S4>(0, "f32/small4"), info_of<CfgF_S8>(1, "f32/small8"), info_of<CfgF_M>(2, "f32/mid"),
+    info_of<CfgF_L>(3, "f32/large"),   info_of<CfgD_S8>(4, "f64/small8"), info_of<CfgD_M>(5, "f64/mid"),
+    info_of<CfgD_L>(6, "f64/large"),
+};
+
+
+// blob layout + padded widths for configuration `ci`
+template <typename real>
+static void plan_blob(PhiPack<real>& P, const CfgInfo& ci) {
+    P.Npm = align_up(P.m, ci.PB);
+    P.Npd = align_up(P.D, ci.PB);
+    int off = 0;
+    auto take = [&](int n) { int o = off; off += align_up(n, 8); return o; };
+    P.off_W1 = take(P.D * P.Npm);
+    for (int l = 0; l < MAXL; ++l) { P.off_Kf[l] = 0; P.off_Kr[l] = 0; P.off_b[l] = 0; }
+    for (int l = 1; l < P.nTh; ++l) { P.off_Kf[l] = take(P.m * P.Npm); P.off_Kr[l] = take(P.m * P.Npm); }
+    P.off_W4 = take(P.m * P.Npd);
+    P.off_sym = take(P.D * P.Npd);
+    for (int l = 0; l < P.nTh; ++l) P.off_b[l] = take(P.m);
+    P.off_w = take(P.m);
+    P.off_cw = take(P.D);
+    P.off_cb = take(1);
+    P.blob_len = off;
+}
+
+// shared-memory panel rows for configuration `ci`; returns bytes of dynamic shared memory
+static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, int d, int m, int nTh, int npm, int npd, int blob_len,
+                        int kind, int nAgents) {
+    const int D = d + 1;
+    const bool inplace = (npm == 1);
+    const bool aliasG = inplace && (npd == 1);
+    int row = 0;
+    auto take = [&](int n) { int o = row; row += n; return o; };
+    sp.U = take(std::max(m, D));
+    sp.U2 = inplace ? sp.U : take(m);
+    for (int i = 0; i < MAXL; ++i) sp.T[i] = 0;
+    sp.T[0] = take(std::max(m, D));
+    for (int i = 1; i <= nTh - 2; ++i) sp.T[i] = take(m);
+    sp.Zb = (nTh > 2) ? take(m) : 0;
+    sp.S = take(D);
+    sp.G = aliasG ? sp.U : take(D);
+    sp.Qs = sp.T[0];
+    sp.Z0 = take(d + 4);
+    sp.ZA = take(d + 4);
+    sp.SC = take(SC_ROWS);
+    sp.RED = take(3 * ci.TPS);
+    sp.PN = take(ci.NWOxWO);
+    sp.QX = (kind == NOC_PROB_QUADCOPTER) ? take(5 * nAgents) : 0;
+    sp.rows = row;
+    sp.wsm_off = align_up(row * ci.TSP, 8);
+    size_t elems = (size_t)sp.wsm_off + (ci.wsmem ? (size_t)blob_len : 0);
+    return elems * ci.elt;
+}
+
+static int g_smem_optin = -1, g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
+int device_facts();
+int sm_count() { device_facts(); return g_sm_count; }
+int device_facts() {
+    if (g_smem_optin >= 0) return NOC_OK;
+    int dev = 0;
+    NOC_CUDA(cudaGetDevice(&dev));
+    int v = 0;
+    NOC_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    NOC_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
+    NOC_CUDA(cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    NOC_CUDA(cudaDeviceGetAttribute(&g_cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    g_smem_optin = v;
+    return NOC_OK;
+}
+
+// candidate configurations in order of preference for (dtype, m); NOC_FORCE_CFG=<id> pins one (tests)
+static std::vector<int> candidates(int dtype, int m) {
+    const char* f = getenv("NOC_FORCE_CFG");
+    if (f && *f) {
+        int id = atoi(f);
+        if (id >= 0 && id < 7 && ((id >= 4) == (dtype == NOC_F64))) return {id};
+    }
+    if (dtype == NOC_F32) {
+        if (m <= 16) return {0, 1, 2, 3};
+        if (m <= 64) return {1, 2, 3};
+        if (m <= 256) return {2, 3};
+        return {3};
+    }
+    if (m <= 64) return {4, 5, 6};
+    if (m <= 256) return {5, 6};
+    return {6};
+}
+
+template <typename real>
+static int dispatch(int cfg_id, const RolloutArgs<real>& A, const PhiRaw<real>* raw, int kmode, size_t smem,
+                    cudaStream_t st, double* out_sums);
+template <>
+int dispatch<float>(int cfg_id, const RolloutArgs<float>& A, const PhiRaw<float>* raw, int kmode, size_t smem,
+                    cudaStream_t st, double* out_sums) {
+    switch (cfg_id) {
+        case 0: return launch_cfg_0(A, raw, kmode, smem, st, out_sums);
+        case 1: return launch_cfg_1(A, raw, kmode, smem, st, out_sums);
+        case 2: return launch_cfg_2(A, raw, kmode, smem, st, out_sums);
+        case 3: return launch_cfg_3(A, raw, kmode, smem, st, out_sums);
+    }
+    return fail(NOC_ERR_ARG, "bad f32 configuration id %d", cfg_id);
+}
+template <>
+int dispatch<double>(int cfg_id, const RolloutArgs<double>& A, const PhiRaw<double>* raw, int kmode, size_t smem,
+                     cudaStream_t st, double* out_sums) {
+    switch (cfg_id) {
+        case 4: return launch_cfg_4(A, raw, kmode, smem, st, out_sums);
+        case 5: return launch_cfg_5(A, raw, kmode, smem, st, out_sums);
+        case 6: return launch_cfg_6(A, raw, kmode, smem, st, out_sums);
+    }
+    return fail(NOC_ERR_ARG, "bad f64 configuration id %d", cfg_id);
+}
+
+static int check_prob(const noc_prob_t* pb, int d, ProbPack& pr) {
+    if (!pb) return fail(NOC_ERR_ARG, "prob is NULL");
+    if (pb->kind < 0 || pb->kind > 2) return fail(NOC_ERR_ARG, "unknown problem kind %d", pb->kind);
+    if (pb->obstacle < 0 || pb->obstacle > 3) return fail(NOC_ERR_ARG, "unknown obstacle %d", pb->obstacle);
+    const int dims[3] = {2, 3, 12};
+    if (pb->agentDim != dims[pb->kind]) return fail(NOC_ERR_ARG, "agentDim %d does not match problem kind %d", pb->agentDim, pb->kind);
+    if (pb->nAgents < 1 || pb->nAgents * pb->agentDim != d)
+        return fail(NOC_ERR_ARG, "nAgents (%d) * agentDim (%d) != d (%d)", pb->nAgents, pb->agentDim, d);
+    if (pb->kind == NOC_PROB_CROSS2D && pb->obstacle == NOC_OBS_BLOCKS) return fail(NOC_ERR_ARG, "'blocks' is a SwarmTraj obstacle");
+    if (pb->kind == NOC_PROB_SWARMTRAJ && (pb->obstacle == NOC_OBS_SOFTCORRIDOR || pb->obstacle == NOC_OBS_HARDCORRIDOR))
+        return fail(NOC_ERR_ARG, "corridor obstacles are Cross2D obstacles");
+    if (pb->kind == NOC_PROB_QUADCOPTER && pb->nAgents > 2 && pb->alph_W > 0.0)
+        return fail(NOC_ERR_UNSUPPORTED, "Quadcopter interaction with more than two agents is broken in the reference "
+                                         "(Quadcopter.py:144-155 slices the batch) and is not reproduced");
+    if (!pb->xtarget) return fail(NOC_ERR_ARG, "prob.xtarget is NULL");
+    pr.kind = pb->kind; pr.obstacle = pb->obstacle; pr.training = pb->training ? 1 : 0;
+    pr.nAgents = pb->nAgents; pr.agentDim = pb->agentDim;
+    pr.nctrl = (pb->kind == NOC_PROB_QUADCOPTER) ? 4 * pb->nAgents : d;
+    pr.alph_Q = pb->alph_Q; pr.alph_W = pb->alph_W; pr.r = pb->r; pr.mass = pb->mass; pr.grav = pb->grav;
+    // interaction cut-off (python double arithmetic, then rounded to the tensor dtype by the comparison)
+    double cut = 2 * pb->r;
+    if (pb->training && pb->kind != NOC_PROB_QUADCOPTER)
+        cut = (pb->kind == NOC_PROB_SWARMTRAJ && pb->nAgents > 2) ? 3.2 * pb->r : 2.2 * pb->r;
+    pr.cutW = cut;
+    pr.xtarget = pb->xtarget;
+    return NOC_OK;
+}
+
+template <typename real>
+static int fill_phi(const noc_phi_t* ph, PhiPack<real>& P, PhiRaw<real>& R) {
+    if (!ph) return fail(NOC_ERR_ARG, "phi is NULL");
+    if (ph->nTh < 2) return fail(NOC_ERR_ARG, "nTh must be an integer >= 2 (src/Phi.py:25-27)");
+    if (ph->nTh > MAXL) return fail(NOC_ERR_UNSUPPORTED, "nTh = %d > %d layers", ph->nTh, MAXL);
+    if (ph->d < 1 || ph->m < 1 || ph->r < 1) return fail(NOC_ERR_ARG, "bad Phi dims d=%d m=%d r=%d", ph->d, ph->m, ph->r);
+    if (!ph->A || !ph->c_w || !ph->c_b || !ph->w || !ph->K || !ph->b) return fail(NOC_ERR_ARG, "phi has NULL tensors");
+    P.d = ph->d; P.D = ph->d + 1; P.m = ph->m; P.nTh = ph->nTh; P.r = ph->r;
+    P.h = (real)((ph->h > 0.0) ? ph->h : 1.0 / (ph->nTh - 1));
+    P.blob = nullptr;
+    R.A = (const real*)ph->A; R.c_w = (const real*)ph->c_w; R.c_b = (const real*)ph->c_b; R.w = (const real*)ph->w;
+    for (int l = 0; l < MAXL; ++l) { R.K[l] = nullptr; R.b[l] = nullptr; }
+    for (int l = 0; l < ph->nTh; ++l) {
+        if (!ph->K[l] || !ph->b[l]) return fail(NOC_ERR_ARG, "phi layer %d has NULL tensors", l);
+        R.K[l] = (const real*)ph->K[l]; R.b[l] = (const real*)ph->b[l];
+    }
+    return NOC_OK;
+}
+
+// choose a configuration whose panels (+ staged weights) fit in shared memory
+template <typename real>
+static int choose(RolloutArgs<real>& A, int dtype, int kind, int nAgents, int& cfg_id, size_t& smem) {
+    int rc = device_facts();
+    if (rc) return rc;
+    std::vector<int> cand = candidates(dtype, A.phi.m);
+    size_t best = 0;
+    for (int id : cand) {
+        const CfgInfo& ci = kCfgs[id];
+        plan_blob(A.phi, ci);
+        smem = plan_smem(A.sp, ci, A.phi.d, A.phi.m, A.phi.nTh, A.phi.Npm / ci.PB, A.phi.Npd / ci.PB, A.phi.blob_len,
+                         kind, nAgents);
+        if (smem <= (size_t)g_smem_optin) { cfg_id = id; return NOC_OK; }
+        best = (best == 0) ? smem : std::min(best, smem);
+    }
+    return fail(NOC_ERR_NOMEM, "Phi (d=%d, m=%d, nTh=%d) needs %zu B of shared memory per tile, device offers %d B",
+                A.phi.d, A.phi.m, A.phi.nTh, best, g_smem_optin);
+}
+
+static void stage_times_host(double t0, double t1, int nt, double* tab) {
+    // replays OCflow.py:25,35,47,50,53 and stepRK4's `h = t1 - t0` (:169) in IEEE double, as Python does
+    volatile double h = (t1 - t0) / nt;
+    volatile double tk = t0;
+    for (int k = 0; k < nt; ++k) {
+        volatile double ta = tk, tb = tk + h;
+        volatile double hh = tb - ta;
+        tk = tk + h;
+        volatile double half = hh / 2;
+        tab[5 * k + 0] = ta;
+        tab[5 * k + 1] = ta + half;
+        tab[5 * k + 2] = ta + hh;
+        tab[5 * k + 3] = tk - h;
+        tab[5 * k + 4] = hh;
+    }
+}
+
+template <typename real>
+static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x, int64_t n, const double* stage_times,
+                       double t0, double t1, int nt, int stepper, const double* alph, int mode, void* out_costs,
+                       void* zFull, void* ctrlFull, cudaStream_t st, int dtype) {
+    RolloutArgs<real> A;
+    memset(&A, 0, sizeof A);
+    PhiRaw<real> R;
+    int rc = fill_phi<real>(ph, A.phi, R);
+    if (rc) return rc;
+    rc = check_prob(pb, ph->d, A.prob);
+    if (rc) return rc;
+    if (!x || n < 1) return fail(NOC_ERR_ARG, "x is NULL or n < 1");
+    if (nt < 1) return fail(NOC_ERR_ARG, "nt must be >= 1");
+    if (!alph) return fail(NOC_ERR_ARG, "alph is NULL");
+    if (stepper != NOC_STEP_NONE && stepper != NOC_STEP_RK1 && stepper != NOC_STEP_RK4)
+        return fail(NOC_ERR_ARG, "stepper must be NOC_STEP_NONE, NOC_STEP_RK1 or NOC_STEP_RK4");
+    if (mode == NOC_MODE_INTERMEDIATES) { if (!zFull || !ctrlFull) return fail(NOC_ERR_ARG, "intermediates mode needs zFull and ctrlFull"); }
+    else if (mode == NOC_MODE_MEAN || mode == NOC_MODE_NOMEAN) { if (!out_costs) return fail(NOC_ERR_ARG, "out_costs is NULL"); }
+    else return fail(NOC_ERR_ARG, "unknown mode %d", mode);
+
+    int cfg_id = -1;
+    size_t smem = 0;
+    rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
+    if (rc) return rc;
+
+    std::vector<double> tab((size_t)nt * 5);
+    if (stage_times) memcpy(tab.data(), stage_times, sizeof(double) * tab.size());
+    else stage_times_host(t0, t1, nt, tab.data());
+    double* dtab = nullptr;
+    NOC_CUDA(cudaMallocAsync((void**)&dtab, sizeof(double) * tab.size(), st));
+    NOC_CUDA(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
+
+    A.x = (const real*)x; A.n = n; A.nt = nt; A.stepper = stepper; A.mode = mode; A.times = dtab;
+    A.alph0 = (real)alph[0]; A.alph3 = (real)alph[3]; A.alph4 = (real)alph[4]; A.alph5 = (real)alph[5];
+    A.t_end = (real)t1;
+    A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
+    A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
+    rc = dispatch<real>(cfg_id, A, &R, KMODE_ROLLOUT, smem, st, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr);
+    cudaError_t e = cudaFreeAsync(dtab, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));
+    return NOC_OK;
+}
+
+template <typename real>
+static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* xh, int64_t n, const double* stage_times,
+                            double t0, double t1, int nt, int stepper, const double* alph, int mode, void* out_h,
+                            void* z_h, void* c_h, cudaStream_t st, int dtype) {
+    if (!ph || !pb) return fail(NOC_ERR_ARG, "phi / prob is NULL");
+    if (!xh || n < 1) return fail(NOC_ERR_ARG, "x is NULL or n < 1");
+    const int d = ph->d;
+    int nctrl = noc_ctrl_dim(pb, d);
+    if (nctrl < 0) return nctrl;
+    size_t xb = sizeof(real) * (size_t)n * d;
+    size_t ob = (mode == NOC_MODE_MEAN) ? sizeof(double) * 8 : (mode == NOC_MODE_NOMEAN ? sizeof(real) * (size_t)n * 8 : 0);
+    size_t zb = (mode == NOC_MODE_INTERMEDIATES) ? sizeof(real) * (size_t)n * (d + 4) * (nt + 1) : 0;
+    size_t cb = (mode == NOC_MODE_INTERMEDIATES) ? sizeof(real) * (size_t)n * nctrl * (nt + 1) : 0;
+    void *xd = nullptr, *od = nullptr, *zd = nullptr, *cd = nullptr;
+    NOC_CUDA(cudaMallocAsync(&xd, xb, st));
+    if (ob) NOC_CUDA(cudaMallocAsync(&od, ob, st));
+    if (zb) NOC_CUDA(cudaMallocAsync(&zd, zb, st));
+    if (cb) NOC_CUDA(cudaMallocAsync(&cd, cb, st));
+    NOC_CUDA(cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, st));
+    int rc = ocflow_impl<real>(ph, pb, xd, n, stage_times, t0, t1, nt, stepper, alph, mode, od, zd, cd, st, dtype);
+    if (rc == NOC_OK) {
+        cudaError_t e = cudaSuccess;
+        if (ob && out_h) e = cudaMemcpyAsync(out_h, od, ob, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && zb && z_h) e = cudaMemcpyAsync(z_h, zd, zb, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess && cb && c_h) e = cudaMemcpyAsync(c_h, cd, cb, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
+    }
+    cudaFreeAsync(xd, st);
+    if (od) cudaFreeAsync(od, st);
+    if (zd) cudaFreeAsync(zd, st);
+    if (cd) cudaFreeAsync(cd, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (rc == NOC_OK && e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "rollout failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+template <typename real>
+static int phi_eval_impl(const noc_phi_t* ph, const void* s, int64_t n, void* out_phi, void* out_grad, cudaStream_t st, int dtype) {
+    RolloutArgs<real> A;
+    memset(&A, 0, sizeof A);
+    PhiRaw<real> R;
+    int rc = fill_phi<real>(ph, A.phi, R);
+    if (rc) return rc;
+    if (!s || n < 1) return fail(NOC_ERR_ARG, "s is NULL or n < 1");
+    int cfg_id = -1;
+    size_t smem = 0;
+    rc = choose<real>(A, dtype, NOC_PROB_CROSS2D, 1, cfg_id, smem);
+    if (rc) return rc;
+    A.x = (const real*)s; A.n = n; A.nt = 0; A.mode = NOC_MODE_NOMEAN;
+    A.out_a = (real*)out_phi; A.out_b = (real*)out_grad;
+    return dispatch<real>(cfg_id, A, &R, KMODE_PHI, smem, st, nullptr);
+}
+
+template <typename real>
+static int prob_eval_impl(const noc_prob_t* pb, const void* x, const void* p, int64_t n, int d, void* o_lhqw, void* o_g,
+                          void* o_c, cudaStream_t st, int dtype) {
+    RolloutArgs<real> A;
+    memset(&A, 0, sizeof A);
+    int rc = check_prob(pb, d, A.prob);
+    if (rc) return rc;
+    if (!x || !p || n < 1) return fail(NOC_ERR_ARG, "x / p is NULL or n < 1");
+    A.phi.d = d; A.phi.D = d + 1; A.phi.m = 1; A.phi.nTh = 2; A.phi.r = 1; A.phi.h = (real)1;
+    int cfg_id = -1;
+    size_t smem = 0;
+    rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
+    if (rc) return rc;
+    A.phi.blob_len = 0;     // no weights are staged or read in this mode
+    A.x = (const real*)x; A.p_in = (const real*)p; A.n = n; A.mode = NOC_MODE_NOMEAN;
+    A.out_a = (real*)o_lhqw; A.out_b = (real*)o_g; A.out_c = (real*)o_c;
+    return dispatch<real>(cfg_id, A, nullptr, KMODE_PROB, smem, st, nullptr);
+}
+
+}  // namespace noc
+
+// ---------------------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------------------
+using namespace noc;
+
+extern "C" {
+
+int noc_version(void) { return NOC_ABI_VERSION; }
+const char* noc_last_error(void) { return g_err.c_str(); }
+int64_t noc_launch_count(void) { return (int64_t)g_launches.load(); }
+
+int noc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes) {
+    int rc = device_facts();
+    if (rc) return rc;
+    if (sm_count) *sm_count = g_sm_count;
+    if (cc_major) *cc_major = g_cc_major;
+    if (cc_minor) *cc_minor = g_cc_minor;
+    if (smem_optin_bytes) *smem_optin_bytes = g_smem_optin;
+    return NOC_OK;
+}
+
+int noc_ctrl_dim(const noc_prob_t* prob, int32_t d) {
+    if (!prob) return fail(NOC_ERR_ARG, "prob is NULL");
+    if (prob->kind == NOC_PROB_QUADCOPTER) return 4 * prob->nAgents;
+    if (prob->kind == NOC_PROB_CROSS2D || prob->kind == NOC_PROB_SWARMTRAJ) return d;
+    return fail(NOC_ERR_ARG, "unknown problem kind %d", prob->kind);
+}
+
+int noc_stage_times(double t0, double t1, int32_t nt, double* table) {
+    if (nt < 1 || !table) return fail(NOC_ERR_ARG, "nt < 1 or table is NULL");
+    stage_times_host(t0, t1, nt, table);
+    return NOC_OK;
+}
+
+int noc_ocflow(const noc_phi_t* phi, const noc_prob_t* prob, const void* x, int64_t n, const double* stage_times, double t0,
+               double t1, int32_t nt, int32_t stepper, const double* alph, int32_t mode, int32_t dtype, void* out_costs,
+               void* zFull, void* ctrlFull, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NOC_F32)
+        return ocflow_impl<float>(phi, prob, x, n, stage_times, t0, t1, nt, stepper, alph, mode, out_costs, zFull, ctrlFull, st, dtype);
+    if (dtype == NOC_F64)
+        return ocflow_impl<double>(phi, prob, x, n, stage_times, t0, t1, nt, stepper, alph, mode, out_costs, zFull, ctrlFull, st, dtype);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
+int noc_ocflow_host(const noc_phi_t* phi, const noc_prob_t* prob, const void* x_host, int64_t n, const double* stage_times,
+                    double t0, double t1, int32_t nt, int32_t stepper, const double* alph, int32_t mode, int32_t dtype,
+                    void* out_costs_host, void* zFull_host, void* ctrlFull_host, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NOC_F32)
+        return ocflow_host_impl<float>(phi, prob, x_host, n, stage_times, t0, t1, nt, stepper, alph, mode, out_costs_host,
+                                       zFull_host, ctrlFull_host, st, dtype);
+    if (dtype == NOC_F64)
+        return ocflow_host_impl<double>(phi, prob, x_host, n, stage_times, t0, t1, nt, stepper, alph, mode, out_costs_host,
+                                        zFull_host, ctrlFull_host, st, dtype);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
+int noc_phi_eval(const noc_phi_t* phi, const void* s, int64_t n, int32_t dtype, void* out_phi, void* out_grad, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NOC_F32) return phi_eval_impl<float>(phi, s, n, out_phi, out_grad, st, dtype);
+    if (dtype == NOC_F64) return phi_eval_impl<double>(phi, s, n, out_phi, out_grad, st, dtype);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
+int noc_prob_eval(const noc_prob_t* prob, const void* x, const void* p, int64_t n, int32_t d, int32_t dtype, void* out_lhqw,
+                  void* out_gradpH, void* out_ctrls, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NOC_F32) return prob_eval_impl<float>(prob, x, p, n, d, out_lhqw, out_gradpH, out_ctrls, st, dtype);
+    if (dtype == NOC_F64) return prob_eval_impl<double>(prob, x, p, n, d, out_lhqw, out_gradpH, out_ctrls, st, dtype);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
+int noc_measure_fma_peak(int32_t dtype, double* tflops) {
+    if (!tflops) return fail(NOC_ERR_ARG, "tflops is NULL");
+    int rc = device_facts();
+    if (rc) return rc;
+    const int blocks = g_sm_count * 8, threads = 256, iters = (dtype == NOC_F64) ? 4096 : 16384;
+    void* out = nullptr;
+    NOC_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    NOC_CUDA(cudaEventCreate(&e0));
+    NOC_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; ++rep) {
+        NOC_CUDA(cudaEventRecord(e0));
+        if (dtype == NOC_F64) fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 1.0000001, 1e-9);
+        else fma_peak_kernel<float><<<blocks, threads>>>((float*)out, iters, 1.0000001f, 1e-9f);
+        count_launch();
+        NOC_CUDA(cudaEventRecord(e1));
+        NOC_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        NOC_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    double flops = 2.0 * 16 * 8 * (double)iters * blocks * threads;
+    *tflops = flops / (best * 1e-3) / 1e12;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return NOC_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,873 @@
+// noc_rollout.cuh — the persistent rollout kernel (FP32 / FP64 FMA register tiles).
+//
+// One launch integrates a whole OCflow call (src/OCflow.py:7-95).  A CTA owns a tile of TS samples for
+// all nt steps: the augmented state z = [x, L, HJt, Q, W] and every hidden vector of Phi live in shared
+// memory as [unit][sample] panels (sample contiguous), each Phi contraction is a register-tiled
+// FMA GEMM (RO outputs x RS samples per thread) whose epilogue applies the activation in registers, and
+// the problem terms (Cross2D / SwarmTraj / Quadcopter) are evaluated per sample between contractions.
+// Nothing but the initial state is read from HBM and nothing but the costs (or, with
+// intermediates=True, the trajectory) is written.
+//
+// Per ODE-function evaluation (ocOdefun, OCflow.py:104-140; Phi.getGrad, Phi.py:99-138), nTh = 2:
+//   GEMM-1  o  = K0 s + b0        ->  u0 = act(o) (panel U), t0 = tanh(o) (panel T0)
+//   GEMM-2  a1 = K1 u0 + b1       ->  y  = tanh(a1) * w           (U, in place)
+//   GEMM-3  z1 = w + h K1' y      ->  v  = t0 * z1                (U, in place)
+//   GEMM-4  g  = K0' v + A'A s + c_w                              (panel G)
+// then L, H, Q, W from (x, p = g[:d]) and the RK combination.  General nTh keeps tanh(a_i) panels.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+#include "noc_types.cuh"
+
+namespace noc {
+
+// ------------------------------------------------------------------------------------------------
+// tile configuration
+// ------------------------------------------------------------------------------------------------
+template <typename real_, int RO_, int RS_, int WO_, int NWO_, int NWS_, bool WSMEM_>
+struct Cfg {
+    using real = real_;
+    static constexpr int RO = RO_;            // outputs per thread
+    static constexpr int RS = RS_;            // samples per thread
+    static constexpr int WO = WO_;            // lanes along outputs
+    static constexpr int WS = 32 / WO_;       // lanes along samples
+    static constexpr int NWO = NWO_;          // warps along outputs
+    static constexpr int NWS = NWS_;          // warps along samples
+    static constexpr int WB = RO * WO;        // outputs per warp
+    static constexpr int PB = WB * NWO;       // outputs per pass of the CTA
+    static constexpr int TS = NWS * WS * RS;  // samples per tile
+    static constexpr int NT = 32 * NWO * NWS; // threads per CTA
+    static constexpr int TPS = NT / TS;       // threads per sample in the problem phase
+    // row padding (in elements) chosen so that the epilogue's 16-byte panel stores of a quarter-warp
+    // fall into distinct banks ("shared-memory panels")
+    static constexpr int PAD = (sizeof(real_) == 4) ? (WO_ >= 8 ? 4 : 8) : (WO_ >= 8 ? 2 : 4);
+    static constexpr int TSP = TS + PAD;
+    static constexpr bool WSMEM = WSMEM_;     // weights staged in shared memory (small nets) or read through L1/L2
+    // a warp owns all outputs of its own samples and one thread owns one sample in the problem phase:
+    // tiles are warp-private and __syncwarp() replaces __syncthreads()
+    static constexpr bool WARP_PRIVATE = (NWO_ == 1) && (TPS == 1);
+    static_assert(NT % TS == 0, "threads per sample must be integral");
+    static_assert(RS_ * sizeof(real_) % 16 == 0 && RO_ * sizeof(real_) % 16 == 0, "16-byte vector tiles");
+};
+
+// packed column of output `o` (see PhiPack): the RO outputs a thread owns are interleaved by WO in
+// output space (so that epilogue stores of neighbouring lanes hit neighbouring panel rows) but
+// contiguous in the packed weight row (so that they load as one vector).
+template <class C>
+__host__ __device__ inline int pack_col(int o) {
+    int pass = o / C::PB, rem = o % C::PB;
+    int wo = rem / C::WB, r2 = rem % C::WB;
+    int ro = r2 / C::WO, lo = r2 % C::WO;
+    return pass * C::PB + wo * C::WB + lo * C::RO + ro;
+}
+
+// ------------------------------------------------------------------------------------------------
+// math: act = antiderivative of tanh (Phi.py:8-9) and tanh, sharing e = exp(-2|x|)
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float r_exp(float x) {
+#ifdef NOC_PRECISE_MATH
+    return expf(x);
+#else
+    return __expf(x);
+#endif
+}
+__device__ __forceinline__ double r_exp(double x) { return exp(x); }
+__device__ __forceinline__ float r_log1pe(float e) {   // log(1 + e), e in [0,1]
+#ifdef NOC_PRECISE_MATH
+    return logf(1.0f + e);
+#else
+    return __logf(1.0f + e);
+#endif
+}
+__device__ __forceinline__ double r_log1pe(double e) { return log(1.0 + e); }
+__device__ __forceinline__ float r_div(float a, float b) {
+#ifdef NOC_PRECISE_MATH
+    return a / b;
+#else
+    return __fdividef(a, b);
+#endif
+}
+__device__ __forceinline__ double r_div(double a, double b) { return a / b; }
+__device__ __forceinline__ float r_sqrt(float x) { return sqrtf(x); }
+__device__ __forceinline__ double r_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ float r_abs(float x) { return fabsf(x); }
+__device__ __forceinline__ double r_abs(double x) { return fabs(x); }
+__device__ __forceinline__ float r_fma(float a, float b, float c) { return fmaf(a, b, c); }
+__device__ __forceinline__ double r_fma(double a, double b, double c) { return fma(a, b, c); }
+__device__ __forceinline__ void r_sincos(float x, float* s, float* c) { sincosf(x, s, c); }
+__device__ __forceinline__ void r_sincos(double x, double* s, double* c) { sincos(x, s, c); }
+
+template <typename real>
+__device__ __forceinline__ void act_tanh(real pre, real& act, real& th) {
+    real a = r_abs(pre);
+    real e = r_exp(real(-2) * a);
+    act = a + r_log1pe(e);
+    th = copysign(r_div(real(1) - e, real(1) + e), pre);
+}
+template <typename real>
+__device__ __forceinline__ real tanh_only(real pre) {
+    real e = r_exp(real(-2) * r_abs(pre));
+    return copysign(r_div(real(1) - e, real(1) + e), pre);
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-byte vector access
+// ------------------------------------------------------------------------------------------------
+template <int N>
+__device__ __forceinline__ void ld_panel(const float* p, float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        float4 t = *reinterpret_cast<const float4*>(p + 4 * i);
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+template <int N>
+__device__ __forceinline__ void ld_panel(const double* p, double (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        double2 t = *reinterpret_cast<const double2*>(p + 2 * i);
+        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
+}
+template <int N>
+__device__ __forceinline__ void ld_weights_global(const float* p, float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i) {
+        float4 t = __ldg(reinterpret_cast<const float4*>(p + 4 * i));
+        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
+    }
+}
+template <int N>
+__device__ __forceinline__ void ld_weights_global(const double* p, double (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) {
+        double2 t = __ldg(reinterpret_cast<const double2*>(p + 2 * i));
+        v[2 * i] = t.x; v[2 * i + 1] = t.y;
+    }
+}
+template <int N>
+__device__ __forceinline__ void st_panel(float* p, const float (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 4; ++i)
+        *reinterpret_cast<float4*>(p + 4 * i) = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+}
+template <int N>
+__device__ __forceinline__ void st_panel(double* p, const double (&v)[N]) {
+#pragma unroll
+    for (int i = 0; i < N / 2; ++i) *reinterpret_cast<double2*>(p + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
+}
+
+template <class C>
+__device__ __forceinline__ void tile_sync() {
+    if (C::WARP_PRIVATE) __syncwarp(); else __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-thread coordinates and panel pointers
+// ------------------------------------------------------------------------------------------------
+template <class C>
+struct ThreadMap {
+    int tid, wo, lo, scol, pcol, orow;
+    __device__ ThreadMap() {
+        tid = threadIdx.x;
+        int warp = tid >> 5, lane = tid & 31;
+        wo = warp % C::NWO;
+        int ws = warp / C::NWO;
+        lo = lane % C::WO;
+        int ls = lane / C::WO;
+        scol = (ws * C::WS + ls) * C::RS;          // first of my RS sample columns
+        pcol = wo * C::WB + lo * C::RO;            // first of my RO packed weight columns (within a pass)
+        orow = wo * C::WB + lo;                    // output row of ro = 0 (within a pass); ro adds ro * WO
+    }
+};
+
+template <typename real>
+struct Panels {
+    real *U, *U2, *T[MAXL], *Zb, *S, *G, *Qs, *Z0, *ZA, *SC, *RED, *PN, *QX;
+    const real* wb;   // weight blob base (shared-memory copy or global)
+};
+
+// acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS)
+template <class C, typename real>
+__device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], const real* __restrict__ W, int ldw,
+                                         const real* __restrict__ in, int K) {
+#pragma unroll 4
+    for (int k = 0; k < K; ++k) {
+        real w[C::RO], a[C::RS];
+        if (C::WSMEM) ld_panel<C::RO>(W + (size_t)k * ldw, w);
+        else ld_weights_global<C::RO>(W + (size_t)k * ldw, w);
+        ld_panel<C::RS>(in + k * C::TSP, a);
+#pragma unroll
+        for (int i = 0; i < C::RO; ++i)
+#pragma unroll
+            for (int j = 0; j < C::RS; ++j) acc[i][j] = r_fma(w[i], a[j], acc[i][j]);
+    }
+}
+
+template <class C, typename real>
+__device__ __forceinline__ void zero_acc(real (&acc)[C::RO][C::RS]) {
+#pragma unroll
+    for (int i = 0; i < C::RO; ++i)
+#pragma unroll
+        for (int j = 0; j < C::RS; ++j) acc[i][j] = real(0);
+}
+
+// ------------------------------------------------------------------------------------------------
+// grad Phi (and, in the TERMINAL pass, the pieces of Phi itself) for the TS samples whose s = [x,t]
+// sits in panel S.  On return panel G holds grad_s Phi (D rows).  TERMINAL additionally leaves
+// partial sums of w . u_{nTh-1} in PN and A'A s in Qs.
+// ------------------------------------------------------------------------------------------------
+template <class C, typename real, bool TERMINAL>
+__device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real>& tp, const ThreadMap<C>& tm) {
+    constexpr int RO = C::RO, RS = C::RS, TSP = C::TSP, PB = C::PB, WO = C::WO;
+    const real* wb = tp.wb;
+    const int npm = P.Npm / PB, npd = P.Npd / PB;
+    real acc[RO][RS];
+
+    // GEMM-1: opening layer (Phi.py:114-115); keeps act(o) in U and tanh(o) in T[0]
+    for (int pass = 0; pass < npm; ++pass) {
+        zero_acc<C>(acc);
+        gemm_acc<C>(acc, wb + P.off_W1 + pass * PB + tm.pcol, P.Npm, tp.S + tm.scol, P.D);
+#pragma unroll
+        for (int ro = 0; ro < RO; ++ro) {
+            int o = pass * PB + tm.orow + ro * WO;
+            if (o < P.m) {
+                real bb = wb[P.off_b[0] + o];
+                real uu[RS], tt[RS];
+#pragma unroll
+                for (int j = 0; j < RS; ++j) act_tanh(acc[ro][j] + bb, uu[j], tt[j]);
+                st_panel<RS>(tp.U + o * TSP + tm.scol, uu);
+                st_panel<RS>(tp.T[0] + o * TSP + tm.scol, tt);
+            }
+        }
+    }
+    tile_sync<C>();
+
+    real* cur = tp.U;
+    real* nxt = tp.U2;
+    real pn[RS];
+#pragma unroll
+    for (int j = 0; j < RS; ++j) pn[j] = real(0);
+
+    // forward ResNet layers (Phi.py:118-120): u_i = u_{i-1} + h act(K_i u_{i-1} + b_i)
+    for (int i = 1; i < P.nTh; ++i) {
+        const bool last = (i == P.nTh - 1);
+        for (int pass = 0; pass < npm; ++pass) {
+            zero_acc<C>(acc);
+            gemm_acc<C>(acc, wb + P.off_Kf[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            if (nxt == cur) tile_sync<C>();      // in place (single pass): every reader of `cur` is done
+#pragma unroll
+            for (int ro = 0; ro < RO; ++ro) {
+                int o = pass * PB + tm.orow + ro * WO;
+                if (o < P.m) {
+                    real bb = wb[P.off_b[i] + o];
+                    real out[RS];
+                    if (!last) {
+                        real uo[RS], tt[RS];
+                        ld_panel<RS>(cur + o * TSP + tm.scol, uo);
+#pragma unroll
+                        for (int j = 0; j < RS; ++j) {
+                            real av;
+                            act_tanh(acc[ro][j] + bb, av, tt[j]);
+                            out[j] = uo[j] + P.h * av;
+                        }
+                        st_panel<RS>(tp.T[i] + o * TSP + tm.scol, tt);
+                    } else {
+                        real wv = wb[P.off_w + o];
+                        if (TERMINAL) {          // Phi.forward needs u_{nTh-1} (Phi.py:96): accumulate w . u_last
+                            real uo[RS];
+                            ld_panel<RS>(cur + o * TSP + tm.scol, uo);
+#pragma unroll
+                            for (int j = 0; j < RS; ++j) {
+                                real av, tv;
+                                act_tanh(acc[ro][j] + bb, av, tv);
+                                pn[j] = r_fma(wv, uo[j] + P.h * av, pn[j]);
+                                out[j] = tv * wv;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < RS; ++j) out[j] = tanh_only(acc[ro][j] + bb) * wv;
+                        }
+                    }
+                    st_panel<RS>(nxt + o * TSP + tm.scol, out);
+                }
+            }
+        }
+        tile_sync<C>();
+        real* t = cur; cur = nxt; nxt = t;
+    }
+    if (TERMINAL) st_panel<RS>(tp.PN + (tm.wo * WO + tm.lo) * TSP + tm.scol, pn);
+
+    // reverse sweep (Phi.py:124-131): z_i = z_{i+1} + h K_i' (tanh(a_i) * z_{i+1}), z_{nTh} = w;
+    // `cur` holds y = tanh(a_i) * z_{i+1}; the epilogue forms the next y with tanh of the layer below.
+    for (int i = P.nTh - 1; i >= 1; --i) {
+        for (int pass = 0; pass < npm; ++pass) {
+            zero_acc<C>(acc);
+            gemm_acc<C>(acc, wb + P.off_Kr[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            if (nxt == cur) tile_sync<C>();
+#pragma unroll
+            for (int ro = 0; ro < RO; ++ro) {
+                int o = pass * PB + tm.orow + ro * WO;
+                if (o < P.m) {
+                    real zi[RS], tt[RS], out[RS];
+                    if (i == P.nTh - 1) {
+                        real wv = wb[P.off_w + o];
+#pragma unroll
+                        for (int j = 0; j < RS; ++j) zi[j] = wv + P.h * acc[ro][j];
+                    } else {
+                        ld_panel<RS>(tp.Zb + o * TSP + tm.scol, zi);
+#pragma unroll
+                        for (int j = 0; j < RS; ++j) zi[j] = zi[j] + P.h * acc[ro][j];
+                    }
+                    if (i > 1) st_panel<RS>(tp.Zb + o * TSP + tm.scol, zi);
+                    ld_panel<RS>(tp.T[i - 1] + o * TSP + tm.scol, tt);
+#pragma unroll
+                    for (int j = 0; j < RS; ++j) out[j] = tt[j] * zi[j];
+                    st_panel<RS>(nxt + o * TSP + tm.scol, out);
+                }
+            }
+        }
+        tile_sync<C>();
+        real* t = cur; cur = nxt; nxt = t;
+    }
+
+    // GEMM-4 (Phi.py:133-136): grad = K0' v + A'A s + c_w'.  The A'A s product is accumulated first so that
+    // the terminal pass can keep it (Phi.forward's quadratic term, Phi.py:96) without a second register tile.
+    for (int pass = 0; pass < npd; ++pass) {
+        zero_acc<C>(acc);
+        gemm_acc<C>(acc, wb + P.off_sym + pass * PB + tm.pcol, P.Npd, tp.S + tm.scol, P.D);
+        if (TERMINAL) {
+#pragma unroll
+            for (int ro = 0; ro < RO; ++ro) {
+                int o = pass * PB + tm.orow + ro * WO;
+                if (o < P.D) st_panel<RS>(tp.Qs + o * TSP + tm.scol, acc[ro]);
+            }
+        }
+        gemm_acc<C>(acc, wb + P.off_W4 + pass * PB + tm.pcol, P.Npd, cur + tm.scol, P.m);
+        if (tp.G == cur) tile_sync<C>();     // G aliases the hidden panel (single pass): readers are done
+#pragma unroll
+        for (int ro = 0; ro < RO; ++ro) {
+            int o = pass * PB + tm.orow + ro * WO;
+            if (o < P.D) {
+                real cw = wb[P.off_cw + o];
+                real g[RS];
+#pragma unroll
+                for (int j = 0; j < RS; ++j) g[j] = acc[ro][j] + cw;
+                st_panel<RS>(tp.G + o * TSP + tm.scol, g);
+            }
+        }
+    }
+    tile_sync<C>();
+}
+
+// ------------------------------------------------------------------------------------------------
+// problem terms
+// ------------------------------------------------------------------------------------------------
+// diagonal Gaussian pdf (src/utils.py:70-86) for a 2-D / 3-D point read from a panel column
+template <typename real>
+__device__ __forceinline__ real gauss2(real x0, real x1, real m0, real m1, real c0, real c1) {
+    const double twopi = 6.283185307179586476925286766559;
+    real den = real(twopi) * r_sqrt(c0 * c1);
+    real e = (x0 - m0) * (x0 - m0) / c0 + (x1 - m1) * (x1 - m1) / c1;
+    return r_exp(real(-0.5) * e) / den;
+}
+template <typename real>
+__device__ __forceinline__ real gauss3(real x0, real x1, real x2, real m0, real m1, real m2, real c0, real c1, real c2) {
+    const double twopi15 = 15.749609945722419;   // (2 pi)^(3/2)
+    real den = real(twopi15) * r_sqrt(c0 * c1 * c2);
+    real e = (x0 - m0) * (x0 - m0) / c0 + (x1 - m1) * (x1 - m1) / c1 + (x2 - m2) * (x2 - m2) / c2;
+    return r_exp(real(-0.5) * e) / den;
+}
+
+// per-agent terrain cost (Cross2D.py:90-119, SwarmTraj.py:90-122); xa points at the agent's first
+// coordinate in panel S (stride TSP between coordinates).  Eval-mode hard obstacles return the 0/1
+// "inside" indicator (the reference returns the boolean mask, F6).
+template <typename real>
+__device__ real terrain_agent(const ProbPack& pr, const real* xa, int stride) {
+    if (pr.obstacle == 1) {             // softcorridor: four Gaussians, cov 0.2
+        real x0 = xa[0], x1 = xa[stride];
+        real c = real(0.2);
+        return ((gauss2<real>(x0, x1, real(-2.5), real(0), c, c) + gauss2<real>(x0, x1, real(2.5), real(0), c, c)) +
+                gauss2<real>(x0, x1, real(-1.5), real(0), c, c)) + gauss2<real>(x0, x1, real(1.5), real(0), c, c);
+    }
+    if (pr.obstacle == 2) {             // hardcorridor: discs of radius 2 (+r in training) around (0,4), (0,-3.5)
+        real x0 = xa[0], x1 = xa[stride];
+        real d1 = r_sqrt(x0 * x0 + (x1 - real(4)) * (x1 - real(4)));
+        real d2 = r_sqrt(x0 * x0 + (x1 + real(3.5)) * (x1 + real(3.5)));
+        if (!pr.training) return (d1 < real(2.0) || d2 < real(2.0)) ? real(1) : real(0);
+        real thr = real(2.0 + pr.r);
+        if (!(d1 < thr || d2 < thr)) return real(0);
+        return gauss2<real>(x0, x1, real(0), real(4), real(1), real(1)) + gauss2<real>(x0, x1, real(0), real(-3.5), real(1), real(1));
+    }
+    if (pr.obstacle == 3) {             // blocks: two boxes
+        real x0 = xa[0], x1 = xa[stride], x2 = xa[2 * stride];
+        if (!pr.training) {
+            bool in = (x0 < real(2.0) && x0 > real(-2.0) && x1 < real(0.5) && x1 > real(-0.5) && x2 < real(7.0)) ||
+                      (x0 < real(4.0) && x0 > real(2.0) && x1 < real(1.0) && x1 > real(-1.0) && x2 < real(4.0));
+            return in ? real(1) : real(0);
+        }
+        double r = pr.r;
+        bool in = (x0 < real(2.0 + r) && x0 > real(-2.0 - r) && x1 < real(0.5 + r) && x1 > real(-0.5 - r) && x2 < real(7.0 + r)) ||
+                  (x0 < real(4.0 + r) && x0 > real(2.0 - r) && x1 < real(1.0 + r) && x1 > real(-1.0 - r) && x2 < real(4.0 + r));
+        if (!in) return real(0);
+        return (gauss3<real>(x0, x1, x2, real(0), real(0), real(2), real(9), real(3), real(9)) +
+                gauss3<real>(x0, x1, x2, real(2.5), real(0), real(2), real(9), real(3), real(3))) + real(999);
+    }
+    return real(0);
+}
+
+// squared distance between agents i and j of one sample (panel column)
+template <typename real>
+__device__ __forceinline__ real pair_dist2(const real* xs, int i, int j, int dim, int stride) {
+    real s = real(0);
+    for (int c = 0; c < dim; ++c) {
+        real df = xs[(i * dim + c) * stride] - xs[(j * dim + c) * stride];
+        s = r_fma(df, df, s);
+    }
+    return s;
+}
+
+// Fills, for every sample of the tile, SC rows L, HJ = |Phi_t - H|, Q, W (and H in row 7), from x in
+// panel S and p = grad_x Phi in panel G (calcLHQW: Cross2D.py:73-87, SwarmTraj.py:71-87,
+// Quadcopter.py:86-113).  Quadcopter also leaves u/mass, f7, f8, f9, u per agent in QX for the
+// dynamics and the controls.
+template <class C, typename real>
+__device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Panels<real>& tp, int tid) {
+    constexpr int TS = C::TS, TSP = C::TSP, TPS = C::TPS;
+    const int s = tid % TS, part = tid / TS;
+    const real* xs = tp.S + s;
+    const real* ps = tp.G + s;
+    real* sc = tp.SC + s;
+
+    if (pr.kind == 2) {                   // ---------------- Quadcopter
+        if (part == 0) {
+            real H = real(0), Q = real(0), W = real(0);
+            real L = real(pr.alph_Q) * Q;
+            if (pr.alph_W > 0.0) {
+                if (pr.nAgents == 2) {    // Quadcopter.py:138-142
+                    real d2 = real(0);
+                    for (int c = 0; c < 3; ++c) { real df = xs[c * TSP] - xs[(12 + c) * TSP]; d2 = r_fma(df, df, d2); }
+                    real dd = r_sqrt(d2);
+                    if (dd < real(2 * pr.r)) W = r_exp(-(dd * dd) / real(2 * pr.r * pr.r));
+                }
+                L = L + real(pr.alph_W) * W;
+            }
+            for (int a = 0; a < pr.nAgents; ++a) {
+                const real* x = xs + a * 12 * TSP;
+                const real* p = ps + a * 12 * TSP;
+                real sps, cps, sth, cth, sph, cph;
+                r_sincos(x[3 * TSP], &sps, &cps);
+                r_sincos(x[4 * TSP], &sth, &cth);
+                r_sincos(x[5 * TSP], &sph, &cph);
+                real f7 = sps * sph + cps * sth * cph;          // Quadcopter.py:190-195
+                real f8 = -cps * sph + sps * sth * cph;
+                real f9 = cth * cph;
+                real p6 = p[6 * TSP], p7 = p[7 * TSP], p8 = p[8 * TSP];
+                real fp = f7 * p6 + f8 * p7 + f9 * p8;
+                real u = real(-1.0 / (2.0 * pr.mass)) * fp;     // calcU, Quadcopter.py:160-163
+                real p9 = p[9 * TSP], p10 = p[10 * TSP], p11 = p[11 * TSP];
+                real sq = p9 * p9 + p10 * p10 + p11 * p11;
+                L = L + real(2) + u * u + real(0.25) * sq;
+                real um = u / real(pr.mass);
+                real xv = x[6 * TSP] * p[0] + x[7 * TSP] * p[1 * TSP] + x[8 * TSP] * p[2 * TSP];
+                real xw = x[9 * TSP] * p[3 * TSP] + x[10 * TSP] * p[4 * TSP] + x[11 * TSP] * p[5 * TSP];
+                H = H - L - xv - xw - um * fp + real(pr.grav) * p8 + real(0.5) * sq;
+                real* qx = tp.QX + (a * 5) * TSP + s;
+                qx[0] = um; qx[TSP] = f7; qx[2 * TSP] = f8; qx[3 * TSP] = f9; qx[4 * TSP] = u;
+            }
+            sc[SC_L * TSP] = L;
+            sc[SC_HJ * TSP] = r_abs(ps[d * TSP] - H);
+            sc[SC_Q * TSP] = Q;
+            sc[SC_W * TSP] = W;
+            sc[7 * TSP] = H;
+        }
+        tile_sync<C>();
+        return;
+    }
+
+    // ---------------- Cross2D / SwarmTraj
+    const int A = pr.nAgents, dim = pr.agentDim;
+    real pp = real(0), q = real(0), w = real(0);
+    for (int r = part; r < d; r += TPS) { real v = ps[r * TSP]; pp = r_fma(v, v, pp); }
+    const bool needQ = (pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0);
+    if (needQ)
+        for (int a = part; a < A; a += TPS) q += terrain_agent<real>(pr, xs + a * dim * TSP, TSP);
+    if (pr.alph_W != 0.0 && A >= 2) {
+        const real cut = real(pr.cutW);
+        const real c2 = real(2 * pr.r * pr.r);
+        if (A == 2) {                     // Cross2D.py:133-145 / SwarmTraj.py:136-145: no "== 1" rule here
+            if (part == 0) {
+                real dd = r_sqrt(pair_dist2<real>(xs, 0, 1, dim, TSP));
+                if (dd < cut) w = r_exp(-(dd * dd) / c2);
+            }
+        } else {                          // Cross2D.py:147-160 / SwarmTraj.py:147-162
+            const real guard = cut * cut * real(1.0001);
+            for (int i = part; i < A; i += TPS) {
+                for (int j = i + 1; j < A; ++j) {
+                    real d2 = pair_dist2<real>(xs, i, j, dim, TSP);
+                    if (d2 < guard) {
+                        real dd = r_sqrt(d2);
+                        if (dd < cut) {
+                            real e = r_exp(-(dd * dd) / c2);
+                            if (e != real(1)) w += e;   // pairs whose Gaussian rounds to 1 are dropped (mask2)
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (TPS > 1) {
+        real* red = tp.RED + s;
+        red[(0 * TPS + part) * TSP] = pp;
+        red[(1 * TPS + part) * TSP] = q;
+        red[(2 * TPS + part) * TSP] = w;
+        __syncthreads();
+        if (part == 0) {
+            pp = red[0]; q = red[(1 * TPS) * TSP]; w = red[(2 * TPS) * TSP];
+            for (int k = 1; k < TPS; ++k) {
+                pp += red[(0 * TPS + k) * TSP]; q += red[(1 * TPS + k) * TSP]; w += red[(2 * TPS + k) * TSP];
+            }
+        }
+    }
+    if (part == 0) {
+        real Qret, L;
+        if (pr.kind == 0) {               // Cross2D returns Q pre-scaled by alph_Q (quirk 6)
+            Qret = real(pr.alph_Q) * q;
+            L = real(0.5) * pp + Qret;
+        } else {
+            Qret = (pr.alph_Q > 0.0) ? q : real(0);
+            L = real(0.5) * pp + real(pr.alph_Q) * Qret;
+        }
+        if (pr.alph_W != 0.0) L = L + real(pr.alph_W) * w; else w = real(0);
+        real H = -L + pp;
+        sc[SC_L * TSP] = L;
+        sc[SC_HJ * TSP] = r_abs(ps[d * TSP] - H);
+        sc[SC_Q * TSP] = Qret;
+        sc[SC_W * TSP] = w;
+        sc[7 * TSP] = H;
+    }
+    tile_sync<C>();
+}
+
+// dx/dt = -grad_p H for state row `row` of sample `s` (Cross2D.py:69-70, SwarmTraj.py:68-69, Quadcopter.py:65-84)
+template <class C, typename real>
+__device__ __forceinline__ real state_rate(const ProbPack& pr, const Panels<real>& tp, int row, int s) {
+    constexpr int TSP = C::TSP;
+    if (pr.kind != 2) return -tp.G[row * TSP + s];
+    int a = row / 12, c = row % 12;
+    if (c < 6) return tp.S[(a * 12 + 6 + c) * TSP + s];
+    if (c < 9) {
+        real um = tp.QX[(a * 5) * TSP + s];
+        real f = tp.QX[(a * 5 + 1 + (c - 6)) * TSP + s];
+        real g = -um * f;
+        if (c == 8) g = g + real(pr.grav);
+        return -g;
+    }
+    return -(real(0.5) * tp.G[row * TSP + s]);
+}
+
+// control channel `c` of sample `s` (calcCtrls: Cross2D.py:164-165, SwarmTraj.py:166-167, Quadcopter.py:165-174)
+template <class C, typename real>
+__device__ __forceinline__ real control_value(const ProbPack& pr, const Panels<real>& tp, int c, int s) {
+    constexpr int TSP = C::TSP;
+    if (pr.kind != 2) return -tp.G[c * TSP + s];
+    int a = c / 4, q = c % 4;
+    if (q == 0) return tp.QX[(a * 5 + 4) * TSP + s];
+    return real(-0.5) * tp.G[(a * 12 + 8 + q) * TSP + s];
+}
+
+// ------------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------------
+template <class C, typename real>
+__device__ __forceinline__ void carve(const RolloutArgs<real>& A, real* base, Panels<real>& tp) {
+    constexpr int TSP = C::TSP;
+    const SmemPlan& sp = A.sp;
+    tp.U = base + sp.U * TSP; tp.U2 = base + sp.U2 * TSP;
+    for (int i = 0; i < MAXL; ++i) tp.T[i] = base + sp.T[i] * TSP;
+    tp.Zb = base + sp.Zb * TSP; tp.S = base + sp.S * TSP; tp.G = base + sp.G * TSP; tp.Qs = base + sp.Qs * TSP;
+    tp.Z0 = base + sp.Z0 * TSP; tp.ZA = base + sp.ZA * TSP; tp.SC = base + sp.SC * TSP; tp.RED = base + sp.RED * TSP;
+    tp.PN = base + sp.PN * TSP; tp.QX = base + sp.QX * TSP;
+    tp.wb = C::WSMEM ? (base + sp.wsm_off) : A.phi.blob;
+}
+
+// S[0..d) <- src[0..d), S[d] <- t
+template <class C, typename real>
+__device__ __forceinline__ void stage_input_from(const Panels<real>& tp, const real* src, int d, real t, int tid) {
+    constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
+    for (int idx = tid; idx < (d + 1) * TS; idx += NT) {
+        int row = idx / TS, s = idx % TS;
+        tp.S[row * TSP + s] = (row < d) ? src[row * TSP + s] : t;
+    }
+}
+
+template <class C, typename real>
+__global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> A, const int kmode) {
+    constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    real* base = reinterpret_cast<real*>(smem_raw);
+    Panels<real> tp;
+    carve<C>(A, base, tp);
+    const ThreadMap<C> tm;
+    const int tid = tm.tid;
+    const PhiPack<real>& P = A.phi;
+    const ProbPack& pr = A.prob;
+    const int d = P.d, D = P.D;
+
+    if (C::WSMEM) {                       // stage the packed weights once per CTA
+        real* wdst = base + A.sp.wsm_off;
+        for (int i = tid; i < P.blob_len; i += NT) wdst[i] = P.blob[i];
+    }
+    __syncthreads();
+
+    double csum = 0.0;                    // threads 0..6: this CTA's running sum of cost q (mean mode)
+    long long cnt = 0;
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const long long s0 = (long long)tile * TS;
+        const int nvalid = (int)((A.n - s0 < TS) ? (A.n - s0) : TS);
+
+        // ---------------------------------------------------------------- evaluation-only modes
+        if (kmode == KMODE_PHI) {         // Phi.forward / Phi.getGrad on rows of s = [x,t]  (Phi.py:91-138)
+            for (int idx = tid; idx < TS * D; idx += NT) {
+                int s = idx / D, c = idx % D;
+                long long gs = s0 + (s < nvalid ? s : nvalid - 1);
+                tp.S[c * TSP + s] = A.x[gs * D + c];
+            }
+            __syncthreads();
+            phi_chain<C, real, true>(P, tp, tm);
+            __syncthreads();
+            for (int s = tid; s < nvalid; s += NT) {
+                if (A.out_a) {
+                    real phiN = real(0), quad = real(0), lin = real(0);
+                    for (int k = 0; k < C::NWO * C::WO; ++k) phiN += tp.PN[k * TSP + s];
+                    for (int o = 0; o < D; ++o) {
+                        real sv = tp.S[o * TSP + s];
+                        quad = r_fma(sv, tp.Qs[o * TSP + s], quad);
+                        lin = r_fma(tp.wb[P.off_cw + o], sv, lin);
+                    }
+                    A.out_a[s0 + s] = phiN + real(0.5) * quad + (lin + tp.wb[P.off_cb]);
+                }
+            }
+            if (A.out_b)
+                for (int idx = tid; idx < nvalid * D; idx += NT) {
+                    int s = idx / D, c = idx % D;
+                    A.out_b[(s0 + s) * D + c] = tp.G[c * TSP + s];
+                }
+            __syncthreads();
+            continue;
+        }
+        if (kmode == KMODE_PROB) {        // calcLHQW / calcGradpH / calcCtrls on rows (x, p)
+            for (int idx = tid; idx < TS * d; idx += NT) {
+                int s = idx / d, c = idx % d;
+                long long gs = s0 + (s < nvalid ? s : nvalid - 1);
+                tp.S[c * TSP + s] = A.x[gs * d + c];
+                tp.G[c * TSP + s] = A.p_in[gs * d + c];
+            }
+            for (int s = tid; s < TS; s += NT) tp.G[d * TSP + s] = real(0);
+            __syncthreads();
+            problem_phase<C>(pr, d, tp, tid);
+            __syncthreads();
+            if (A.out_a)
+                for (int s = tid; s < nvalid; s += NT) {
+                    real* o = A.out_a + (s0 + s) * 4;
+                    o[0] = tp.SC[SC_L * TSP + s]; o[1] = tp.SC[7 * TSP + s];
+                    o[2] = tp.SC[SC_Q * TSP + s]; o[3] = tp.SC[SC_W * TSP + s];
+                }
+            if (A.out_b)
+                for (int idx = tid; idx < nvalid * d; idx += NT) {
+                    int s = idx / d, c = idx % d;
+                    A.out_b[(s0 + s) * d + c] = -state_rate<C>(pr, tp, c, s);
+                }
+            if (A.out_c)
+                for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
+                    int s = idx / pr.nctrl, c = idx % pr.nctrl;
+                    A.out_c[(s0 + s) * pr.nctrl + c] = control_value<C>(pr, tp, c, s);
+                }
+            __syncthreads();
+            continue;
+        }
+
+        // ---------------------------------------------------------------- rollout (OCflow.py:7-95)
+        real* Z0 = tp.Z0;
+        real* ZA = tp.ZA;
+        for (int idx = tid; idx < TS * d; idx += NT) {       // z = [x, 0, 0, 0, 0]  (OCflow.py:33)
+            int s = idx / d, c = idx % d;
+            long long gs = s0 + (s < nvalid ? s : nvalid - 1);   // padding samples replay the last valid one
+            Z0[c * TSP + s] = A.x[gs * d + c];
+        }
+        for (int idx = tid; idx < 4 * TS; idx += NT) Z0[(d + idx / TS) * TSP + idx % TS] = real(0);
+        __syncthreads();
+
+        const bool inter = (A.mode == 2);
+        const int ntp1 = A.nt + 1;
+        if (inter) {                                          // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
+            for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
+                int s = idx / (d + 4), row = idx % (d + 4);
+                A.out_b[((s0 + s) * (d + 4) + row) * ntp1] = Z0[row * TSP + s];
+            }
+            for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
+                int s = idx / pr.nctrl, c = idx % pr.nctrl;
+                A.out_c[((s0 + s) * pr.nctrl + c) * ntp1] = real(0);
+            }
+        }
+
+        const int nstage = (A.stepper == 4) ? 4 : (A.stepper == 1 ? 1 : 0);
+        for (int k = 0; k < A.nt; ++k) {
+            const double* tt = A.times + 5 * k;
+            const real hstep = real(tt[4]);                   // h = t1 - t0 recomputed per step (OCflow.py:169)
+            if (nstage > 0) {
+                stage_input_from<C>(tp, Z0, d, real(tt[0]), tid);
+                tile_sync<C>();
+            }
+            for (int st = 0; st < nstage; ++st) {
+                // RK4 weights (OCflow.py:172-182); python doubles rounded to the tensor dtype
+                real wgt, cnext, tnext;
+                if (nstage == 1) { wgt = real(1); cnext = real(0); tnext = real(0); }
+                else if (st == 0) { wgt = real(1.0 / 6.0); cnext = real(0.5); tnext = real(tt[1]); }
+                else if (st == 1) { wgt = real(2.0 / 6.0); cnext = real(0.5); tnext = real(tt[1]); }
+                else if (st == 2) { wgt = real(2.0 / 6.0); cnext = real(1.0); tnext = real(tt[2]); }
+                else { wgt = real(1.0 / 6.0); cnext = real(0); tnext = real(0); }
+                const bool lastst = (st == nstage - 1);
+
+                phi_chain<C, real, false>(P, tp, tm);        // G <- grad Phi([x_stage, t])
+                problem_phase<C>(pr, d, tp, tid);            // SC <- L, |Phi_t - H|, Q, W
+
+                if (pr.kind == 2) {                           // Quadcopter rates read other rows of S: K first, then update
+                    for (int idx = tid; idx < d * TS; idx += NT) {
+                        int row = idx / TS, s = idx % TS;
+                        real f = state_rate<C>(pr, tp, row, s);
+                        tp.G[row * TSP + s] = hstep * f;
+                    }
+                    tile_sync<C>();
+                }
+                for (int idx = tid; idx < (d + 4) * TS; idx += NT) {
+                    int row = idx / TS, s = idx % TS;
+                    real kk;
+                    if (row >= d) kk = hstep * tp.SC[(row - d) * TSP + s];
+                    else if (pr.kind == 2) kk = tp.G[row * TSP + s];
+                    else kk = hstep * (-tp.G[row * TSP + s]);
+                    real z0v = Z0[row * TSP + s];
+                    real zprev = (st == 0) ? z0v : ZA[row * TSP + s];
+                    ZA[row * TSP + s] = zprev + wgt * kk;
+                    if (!lastst && row < d) tp.S[row * TSP + s] = z0v + cnext * kk;
+                }
+                if (!lastst)
+                    for (int s = tid; s < TS; s += NT) tp.S[d * TSP + s] = tnext;
+                tile_sync<C>();
+            }
+            if (nstage > 0) { real* t = Z0; Z0 = ZA; ZA = t; }
+
+            if (inter) {                                      // OCflow.py:51-55
+                __syncthreads();
+                for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
+                    int s = idx / (d + 4), row = idx % (d + 4);
+                    A.out_b[((s0 + s) * (d + 4) + row) * ntp1 + (k + 1)] = Z0[row * TSP + s];
+                }
+                stage_input_from<C>(tp, Z0, d, real(tt[3]), tid);   // new state, OLD time (quirk 3)
+                __syncthreads();
+                phi_chain<C, real, false>(P, tp, tm);
+                if (pr.kind == 2) problem_phase<C>(pr, d, tp, tid);
+                __syncthreads();
+                for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
+                    int s = idx / pr.nctrl, c = idx % pr.nctrl;
+                    A.out_c[((s0 + s) * pr.nctrl + c) * ntp1 + (k + 1)] = control_value<C>(pr, tp, c, s);
+                }
+                __syncthreads();
+            }
+        }
+
+        // ---------------------------------------------------------------- terminal block (OCflow.py:58-90)
+        __syncthreads();
+        stage_input_from<C>(tp, Z0, d, A.t_end, tid);
+        __syncthreads();
+        phi_chain<C, real, true>(P, tp, tm);
+        __syncthreads();
+        const real* xt = static_cast<const real*>(pr.xtarget);
+        for (int s = tid; s < TS; s += NT) {
+            real cG = real(0), hjg = real(0);
+            for (int r = 0; r < d; ++r) {
+                real res = Z0[r * TSP + s] - xt[r];
+                cG = r_fma(res, res, cG);
+                hjg += r_abs(tp.G[r * TSP + s] - A.alph0 * res);
+            }
+            cG = real(0.5) * cG;
+            real phiN = real(0), quad = real(0), lin = real(0);
+            for (int k = 0; k < C::NWO * C::WO; ++k) phiN += tp.PN[k * TSP + s];
+            for (int o = 0; o < D; ++o) {
+                real sv = tp.S[o * TSP + s];
+                quad = r_fma(sv, tp.Qs[o * TSP + s], quad);
+                lin = r_fma(tp.wb[P.off_cw + o], sv, lin);
+            }
+            real phi1 = phiN + real(0.5) * quad + (lin + tp.wb[P.off_cb]);
+            real* sc = tp.SC + s;
+            sc[0 * TSP] = Z0[d * TSP + s];                    // L
+            sc[1 * TSP] = cG;                                 // G
+            sc[2 * TSP] = Z0[(d + 1) * TSP + s];              // HJt
+            sc[3 * TSP] = r_abs(phi1 - A.alph0 * cG);         // HJfin
+            sc[4 * TSP] = hjg;                                // HJgrad
+            sc[5 * TSP] = Z0[(d + 2) * TSP + s];              // Q
+            sc[6 * TSP] = Z0[(d + 3) * TSP + s];              // W
+        }
+        __syncthreads();
+        if (A.mode == 0) {
+            if (tid < 7) for (int s = 0; s < nvalid; ++s) csum += (double)tp.SC[tid * TSP + s];
+            cnt += nvalid;
+        } else if (A.mode == 1) {
+            for (int s = tid; s < nvalid; s += NT) {
+                const real* sc = tp.SC + s;
+                real L = sc[0], Gc = sc[TSP], HJt = sc[2 * TSP], HJf = sc[3 * TSP], HJg = sc[4 * TSP];
+                real* o = A.out_a + (s0 + s) * 8;
+                o[0] = L + A.alph0 * Gc + A.alph3 * HJt + A.alph4 * HJf + A.alph5 * HJg;   // OCflow.py:75
+                o[1] = L; o[2] = Gc; o[3] = HJt; o[4] = HJf; o[5] = HJg; o[6] = sc[5 * TSP]; o[7] = sc[6 * TSP];
+            }
+        }
+        __syncthreads();
+    }
+
+    if (kmode == KMODE_ROLLOUT && A.mode == 0 && A.partials) {
+        if (tid < 7) A.partials[blockIdx.x * 8 + tid] = csum;
+        if (tid == 7) A.partials[blockIdx.x * 8 + 7] = (double)cnt;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight packing: reference layout (nn.Linear, y = x W' + b) -> K-major, output-permuted, zero-padded
+// ------------------------------------------------------------------------------------------------
+// (the host zero-fills the blob with cudaMemsetAsync first: padding columns are zero weights)
+template <class C, typename real>
+__global__ void pack_phi_kernel(const PhiRaw<real> R, const PhiPack<real> P, real* __restrict__ blob) {
+    const int D = P.D, m = P.m, nTh = P.nTh, r = P.r;
+    const int stride = gridDim.x * blockDim.x;
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    // W1[k][pc(o)] = K0[o][k]            W4[j][pc(o)] = K0[j][o]
+    for (int i = t0; i < m * D; i += stride) {
+        int o = i / D, k = i % D;
+        real v = R.K[0][i];
+        blob[P.off_W1 + k * P.Npm + pack_col<C>(o)] = v;
+        blob[P.off_W4 + o * P.Npd + pack_col<C>(k)] = v;
+    }
+    // Kf_i[k][pc(o)] = K_i[o][k]         Kr_i[j][pc(k)] = K_i[j][k]
+    for (int l = 1; l < nTh; ++l)
+        for (int i = t0; i < m * m; i += stride) {
+            int o = i / m, k = i % m;
+            real v = R.K[l][i];
+            blob[P.off_Kf[l] + k * P.Npm + pack_col<C>(o)] = v;
+            blob[P.off_Kr[l] + o * P.Npm + pack_col<C>(k)] = v;
+        }
+    // sym[k][pc(o)] = sum_q A[q][k] A[q][o]   (A'A, Phi.py:110)
+    for (int i = t0; i < D * D; i += stride) {
+        int k = i / D, o = i % D;
+        real s = real(0);
+        for (int q = 0; q < r; ++q) s = r_fma(R.A[q * D + k], R.A[q * D + o], s);
+        blob[P.off_sym + k * P.Npd + pack_col<C>(o)] = s;
+    }
+    for (int l = 0; l < nTh; ++l)
+        for (int i = t0; i < m; i += stride) blob[P.off_b[l] + i] = R.b[l][i];
+    for (int i = t0; i < m; i += stride) blob[P.off_w + i] = R.w[i];
+    for (int i = t0; i < D; i += stride) blob[P.off_cw + i] = R.c_w[i];
+    if (t0 == 0) blob[P.off_cb] = R.c_b[0];
+}
+
+}  // namespace noc

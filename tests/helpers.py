@@ -44,3 +44,32 @@ def rel_err(a, b, floor=0.0):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return float(np.max(np.abs(a - b) / np.maximum(np.abs(b), max(floor, 1e-300))))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# product-side set-up (neuraloc_b200 host mirrors); importing is CPU-safe, calling needs the GPU
+# ---------------------------------------------------------------------------------------------------------
+def product_setup(name, dtype, device="cuda"):
+    """-> (net, prob, xInit, meta) built exactly like evalOC.py:51-64 but from the committed checkpoint fixtures."""
+    import neuraloc_b200 as nb
+    sd, meta = load_ckpt(name)
+    cvt = lambda v: v.to(dtype).to(device)
+    prob, x0, _, xinit = nb.initProb(meta["data"], 4, 4, var0=1.0, alph=meta["alph"], cvt=cvt)
+    prob.eval()
+    net = nb.Phi(nTh=meta["nTh"], m=meta["m"], d=x0.shape[1], alph=meta["alph"])
+    net.load_state_dict(sd)
+    net = net.to(dtype).to(device)
+    net.eval()
+    return net, prob, xinit, meta
+
+
+def mean_vec(out):
+    Jc, cs = out
+    return np.array([float(Jc)] + [float(c) for c in cs])
+
+
+def check_costs(got, ref, rel, abs_floor, what=""):
+    got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
+    err = np.abs(got - ref)
+    ok = (err <= rel * np.abs(ref)) | (err <= abs_floor)
+    assert ok.all(), "%s: got %s ref %s relerr %s" % (what, got, ref, err / np.maximum(np.abs(ref), 1e-300))
