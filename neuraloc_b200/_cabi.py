@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnoc_b200.so")
+LIB_PATH = os.environ.get("NOC_LIB") or os.path.join(_HERE, "libnoc_b200.so")   # NOC_LIB: alternative build (tests)
 
 F32, F64 = 0, 1
 PROB_KINDS = {"Cross2D": 0, "SwarmTraj": 1, "Quadcopter": 2}

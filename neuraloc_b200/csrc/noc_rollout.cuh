@@ -182,26 +182,61 @@ struct ThreadMap {
     }
 };
 
-template <typename real>
+// Element offsets of every panel from the dynamic shared-memory base.  Device functions rebuild their
+// pointers as `smem_base<real>() + offset` so that the compiler keeps them in the shared address space
+// (LDS/STS) even inside non-inlined functions; pointers fetched from a struct would decay to generic LD/ST.
 struct Panels {
-    real *U, *U2, *T[MAXL], *Zb, *S, *G, *Qs, *Z0, *ZA, *SC, *RED, *PN, *QX;
-    const real* wb;   // weight blob base (shared-memory copy or global)
+    int U, U2, T[MAXL], Zb, S, G, Qs, Z0, ZA, SC, RED, PN, QX;
+    int W;            // staged weight blob (WSMEM configurations)
 };
 
-// acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS)
+extern __shared__ __align__(16) unsigned char noc_smem_raw[];
+template <typename real>
+__device__ __forceinline__ real* smem_base() { return reinterpret_cast<real*>(noc_smem_raw); }
+
+// scalar weight read: staged copy (shared) or the global blob through the read-only path
 template <class C, typename real>
-__device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], const real* __restrict__ W, int ldw,
-                                         const real* __restrict__ in, int K) {
-#pragma unroll 4
-    for (int k = 0; k < K; ++k) {
-        real w[C::RO], a[C::RS];
-        if (C::WSMEM) ld_panel<C::RO>(W + (size_t)k * ldw, w);
-        else ld_weights_global<C::RO>(W + (size_t)k * ldw, w);
-        ld_panel<C::RS>(in + k * C::TSP, a);
+__device__ __forceinline__ real wload(const real* __restrict__ gblob, int idx) {
+    if (C::WSMEM) return smem_base<real>()[idx];     // caller adds tp.W to idx
+    return __ldg(gblob + idx);
+}
+
+// acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS)
+// `woff` / `in_off` are element offsets: weights from the staged copy (WSMEM) or the global blob, inputs from a panel.
+// Software-pipelined in registers: weights run 4 k-steps ahead (they may come from L2), the activation panel row
+// one step ahead (shared memory), so that every FFMA block overlaps the loads of later steps.  Loads past K are
+// clamped to row K-1 (valid memory, unused), the FFMA block of a step past K is skipped.
+template <class C, typename real>
+__device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], const real* __restrict__ gblob, int woff, int ldw,
+                                         int in_off, int K) {
+    constexpr int PF = 4;
+    const real* in = smem_base<real>() + in_off;
+    const real* W = C::WSMEM ? (smem_base<real>() + woff) : (gblob + woff);
+    real wq[PF][C::RO], a[2][C::RS];
+    const int kl = K - 1;
 #pragma unroll
-        for (int i = 0; i < C::RO; ++i)
+    for (int u = 0; u < PF; ++u) {
+        const int kk = (u < kl) ? u : kl;
+        if (C::WSMEM) ld_panel<C::RO>(W + kk * ldw, wq[u]);
+        else ld_weights_global<C::RO>(W + kk * ldw, wq[u]);
+    }
+    ld_panel<C::RS>(in, a[0]);
+    for (int k = 0; k < K; k += PF) {
 #pragma unroll
-            for (int j = 0; j < C::RS; ++j) acc[i][j] = r_fma(w[i], a[j], acc[i][j]);
+        for (int u = 0; u < PF; ++u) {
+            const int kk = k + u;
+            const int kn = (kk + 1 < kl) ? kk + 1 : kl;
+            ld_panel<C::RS>(in + kn * C::TSP, a[(u + 1) & 1]);
+            if (kk < K) {
+#pragma unroll
+                for (int i = 0; i < C::RO; ++i)
+#pragma unroll
+                    for (int j = 0; j < C::RS; ++j) acc[i][j] = r_fma(wq[u][i], a[u & 1][j], acc[i][j]);
+            }
+            const int kw = (kk + PF < kl) ? kk + PF : kl;
+            if (C::WSMEM) ld_panel<C::RO>(W + kw * ldw, wq[u]);
+            else ld_weights_global<C::RO>(W + kw * ldw, wq[u]);
+        }
     }
 }
 
@@ -219,33 +254,34 @@ __device__ __forceinline__ void zero_acc(real (&acc)[C::RO][C::RS]) {
 // partial sums of w . u_{nTh-1} in PN and A'A s in Qs.
 // ------------------------------------------------------------------------------------------------
 template <class C, typename real, bool TERMINAL>
-__device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real>& tp, const ThreadMap<C>& tm) {
+__device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp, const ThreadMap<C>& tm) {
     constexpr int RO = C::RO, RS = C::RS, TSP = C::TSP, PB = C::PB, WO = C::WO;
-    const real* wb = tp.wb;
+    real* sm = smem_base<real>();
+    const real* gb = P.blob;
+    const int wbase = C::WSMEM ? tp.W : 0;          // scalar weights: staged copy or global blob
     const int npm = P.Npm / PB, npd = P.Npd / PB;
     real acc[RO][RS];
 
     // GEMM-1: opening layer (Phi.py:114-115); keeps act(o) in U and tanh(o) in T[0]
     for (int pass = 0; pass < npm; ++pass) {
         zero_acc<C>(acc);
-        gemm_acc<C>(acc, wb + P.off_W1 + pass * PB + tm.pcol, P.Npm, tp.S + tm.scol, P.D);
+        gemm_acc<C>(acc, gb, wbase + P.off_W1 + pass * PB + tm.pcol, P.Npm, tp.S + tm.scol, P.D);
 #pragma unroll
         for (int ro = 0; ro < RO; ++ro) {
             int o = pass * PB + tm.orow + ro * WO;
             if (o < P.m) {
-                real bb = wb[P.off_b[0] + o];
+                real bb = wload<C>(gb, wbase + P.off_b[0] + o);
                 real uu[RS], tt[RS];
 #pragma unroll
                 for (int j = 0; j < RS; ++j) act_tanh(acc[ro][j] + bb, uu[j], tt[j]);
-                st_panel<RS>(tp.U + o * TSP + tm.scol, uu);
-                st_panel<RS>(tp.T[0] + o * TSP + tm.scol, tt);
+                st_panel<RS>(sm + tp.U + o * TSP + tm.scol, uu);
+                st_panel<RS>(sm + tp.T[0] + o * TSP + tm.scol, tt);
             }
         }
     }
     tile_sync<C>();
 
-    real* cur = tp.U;
-    real* nxt = tp.U2;
+    int cur = tp.U, nxt = tp.U2;
     real pn[RS];
 #pragma unroll
     for (int j = 0; j < RS; ++j) pn[j] = real(0);
@@ -255,29 +291,29 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real
         const bool last = (i == P.nTh - 1);
         for (int pass = 0; pass < npm; ++pass) {
             zero_acc<C>(acc);
-            gemm_acc<C>(acc, wb + P.off_Kf[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            gemm_acc<C>(acc, gb, wbase + P.off_Kf[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
             if (nxt == cur) tile_sync<C>();      // in place (single pass): every reader of `cur` is done
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
                 int o = pass * PB + tm.orow + ro * WO;
                 if (o < P.m) {
-                    real bb = wb[P.off_b[i] + o];
+                    real bb = wload<C>(gb, wbase + P.off_b[i] + o);
                     real out[RS];
                     if (!last) {
                         real uo[RS], tt[RS];
-                        ld_panel<RS>(cur + o * TSP + tm.scol, uo);
+                        ld_panel<RS>(sm + cur + o * TSP + tm.scol, uo);
 #pragma unroll
                         for (int j = 0; j < RS; ++j) {
                             real av;
                             act_tanh(acc[ro][j] + bb, av, tt[j]);
                             out[j] = uo[j] + P.h * av;
                         }
-                        st_panel<RS>(tp.T[i] + o * TSP + tm.scol, tt);
+                        st_panel<RS>(sm + tp.T[i] + o * TSP + tm.scol, tt);
                     } else {
-                        real wv = wb[P.off_w + o];
+                        real wv = wload<C>(gb, wbase + P.off_w + o);
                         if (TERMINAL) {          // Phi.forward needs u_{nTh-1} (Phi.py:96): accumulate w . u_last
                             real uo[RS];
-                            ld_panel<RS>(cur + o * TSP + tm.scol, uo);
+                            ld_panel<RS>(sm + cur + o * TSP + tm.scol, uo);
 #pragma unroll
                             for (int j = 0; j < RS; ++j) {
                                 real av, tv;
@@ -290,21 +326,21 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real
                             for (int j = 0; j < RS; ++j) out[j] = tanh_only(acc[ro][j] + bb) * wv;
                         }
                     }
-                    st_panel<RS>(nxt + o * TSP + tm.scol, out);
+                    st_panel<RS>(sm + nxt + o * TSP + tm.scol, out);
                 }
             }
         }
         tile_sync<C>();
-        real* t = cur; cur = nxt; nxt = t;
+        int t = cur; cur = nxt; nxt = t;
     }
-    if (TERMINAL) st_panel<RS>(tp.PN + (tm.wo * WO + tm.lo) * TSP + tm.scol, pn);
+    if (TERMINAL) st_panel<RS>(sm + tp.PN + (tm.wo * WO + tm.lo) * TSP + tm.scol, pn);
 
     // reverse sweep (Phi.py:124-131): z_i = z_{i+1} + h K_i' (tanh(a_i) * z_{i+1}), z_{nTh} = w;
     // `cur` holds y = tanh(a_i) * z_{i+1}; the epilogue forms the next y with tanh of the layer below.
     for (int i = P.nTh - 1; i >= 1; --i) {
         for (int pass = 0; pass < npm; ++pass) {
             zero_acc<C>(acc);
-            gemm_acc<C>(acc, wb + P.off_Kr[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            gemm_acc<C>(acc, gb, wbase + P.off_Kr[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
             if (nxt == cur) tile_sync<C>();
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
@@ -312,49 +348,49 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real
                 if (o < P.m) {
                     real zi[RS], tt[RS], out[RS];
                     if (i == P.nTh - 1) {
-                        real wv = wb[P.off_w + o];
+                        real wv = wload<C>(gb, wbase + P.off_w + o);
 #pragma unroll
                         for (int j = 0; j < RS; ++j) zi[j] = wv + P.h * acc[ro][j];
                     } else {
-                        ld_panel<RS>(tp.Zb + o * TSP + tm.scol, zi);
+                        ld_panel<RS>(sm + tp.Zb + o * TSP + tm.scol, zi);
 #pragma unroll
                         for (int j = 0; j < RS; ++j) zi[j] = zi[j] + P.h * acc[ro][j];
                     }
-                    if (i > 1) st_panel<RS>(tp.Zb + o * TSP + tm.scol, zi);
-                    ld_panel<RS>(tp.T[i - 1] + o * TSP + tm.scol, tt);
+                    if (i > 1) st_panel<RS>(sm + tp.Zb + o * TSP + tm.scol, zi);
+                    ld_panel<RS>(sm + tp.T[i - 1] + o * TSP + tm.scol, tt);
 #pragma unroll
                     for (int j = 0; j < RS; ++j) out[j] = tt[j] * zi[j];
-                    st_panel<RS>(nxt + o * TSP + tm.scol, out);
+                    st_panel<RS>(sm + nxt + o * TSP + tm.scol, out);
                 }
             }
         }
         tile_sync<C>();
-        real* t = cur; cur = nxt; nxt = t;
+        int t = cur; cur = nxt; nxt = t;
     }
 
     // GEMM-4 (Phi.py:133-136): grad = K0' v + A'A s + c_w'.  The A'A s product is accumulated first so that
     // the terminal pass can keep it (Phi.forward's quadratic term, Phi.py:96) without a second register tile.
     for (int pass = 0; pass < npd; ++pass) {
         zero_acc<C>(acc);
-        gemm_acc<C>(acc, wb + P.off_sym + pass * PB + tm.pcol, P.Npd, tp.S + tm.scol, P.D);
+        gemm_acc<C>(acc, gb, wbase + P.off_sym + pass * PB + tm.pcol, P.Npd, tp.S + tm.scol, P.D);
         if (TERMINAL) {
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
                 int o = pass * PB + tm.orow + ro * WO;
-                if (o < P.D) st_panel<RS>(tp.Qs + o * TSP + tm.scol, acc[ro]);
+                if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
             }
         }
-        gemm_acc<C>(acc, wb + P.off_W4 + pass * PB + tm.pcol, P.Npd, cur + tm.scol, P.m);
+        gemm_acc<C>(acc, gb, wbase + P.off_W4 + pass * PB + tm.pcol, P.Npd, cur + tm.scol, P.m);
         if (tp.G == cur) tile_sync<C>();     // G aliases the hidden panel (single pass): readers are done
 #pragma unroll
         for (int ro = 0; ro < RO; ++ro) {
             int o = pass * PB + tm.orow + ro * WO;
             if (o < P.D) {
-                real cw = wb[P.off_cw + o];
+                real cw = wload<C>(gb, wbase + P.off_cw + o);
                 real g[RS];
 #pragma unroll
                 for (int j = 0; j < RS; ++j) g[j] = acc[ro][j] + cw;
-                st_panel<RS>(tp.G + o * TSP + tm.scol, g);
+                st_panel<RS>(sm + tp.G + o * TSP + tm.scol, g);
             }
         }
     }
@@ -364,7 +400,7 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels<real
 // ------------------------------------------------------------------------------------------------
 // problem terms
 // ------------------------------------------------------------------------------------------------
-// diagonal Gaussian pdf (src/utils.py:70-86) for a 2-D / 3-D point read from a panel column
+// diagonal Gaussian pdf (src/utils.py:70-86) for a 2-D / 3-D point
 template <typename real>
 __device__ __forceinline__ real gauss2(real x0, real x1, real m0, real m1, real c0, real c1) {
     const double twopi = 6.283185307179586476925286766559;
@@ -380,19 +416,16 @@ __device__ __forceinline__ real gauss3(real x0, real x1, real x2, real m0, real 
     return r_exp(real(-0.5) * e) / den;
 }
 
-// per-agent terrain cost (Cross2D.py:90-119, SwarmTraj.py:90-122); xa points at the agent's first
-// coordinate in panel S (stride TSP between coordinates).  Eval-mode hard obstacles return the 0/1
-// "inside" indicator (the reference returns the boolean mask, F6).
+// per-agent terrain cost (Cross2D.py:90-119, SwarmTraj.py:90-122) at the agent position (x0, x1[, x2]).
+// Eval-mode hard obstacles return the 0/1 "inside" indicator (the reference returns the boolean mask, F6).
 template <typename real>
-__device__ real terrain_agent(const ProbPack& pr, const real* xa, int stride) {
+__device__ real terrain_agent(const ProbPack& pr, real x0, real x1, real x2) {
     if (pr.obstacle == 1) {             // softcorridor: four Gaussians, cov 0.2
-        real x0 = xa[0], x1 = xa[stride];
         real c = real(0.2);
         return ((gauss2<real>(x0, x1, real(-2.5), real(0), c, c) + gauss2<real>(x0, x1, real(2.5), real(0), c, c)) +
                 gauss2<real>(x0, x1, real(-1.5), real(0), c, c)) + gauss2<real>(x0, x1, real(1.5), real(0), c, c);
     }
     if (pr.obstacle == 2) {             // hardcorridor: discs of radius 2 (+r in training) around (0,4), (0,-3.5)
-        real x0 = xa[0], x1 = xa[stride];
         real d1 = r_sqrt(x0 * x0 + (x1 - real(4)) * (x1 - real(4)));
         real d2 = r_sqrt(x0 * x0 + (x1 + real(3.5)) * (x1 + real(3.5)));
         if (!pr.training) return (d1 < real(2.0) || d2 < real(2.0)) ? real(1) : real(0);
@@ -401,7 +434,6 @@ __device__ real terrain_agent(const ProbPack& pr, const real* xa, int stride) {
         return gauss2<real>(x0, x1, real(0), real(4), real(1), real(1)) + gauss2<real>(x0, x1, real(0), real(-3.5), real(1), real(1));
     }
     if (pr.obstacle == 3) {             // blocks: two boxes
-        real x0 = xa[0], x1 = xa[stride], x2 = xa[2 * stride];
         if (!pr.training) {
             bool in = (x0 < real(2.0) && x0 > real(-2.0) && x1 < real(0.5) && x1 > real(-0.5) && x2 < real(7.0)) ||
                       (x0 < real(4.0) && x0 > real(2.0) && x1 < real(1.0) && x1 > real(-1.0) && x2 < real(4.0));
@@ -417,15 +449,45 @@ __device__ real terrain_agent(const ProbPack& pr, const real* xa, int stride) {
     return real(0);
 }
 
-// squared distance between agents i and j of one sample (panel column)
-template <typename real>
-__device__ __forceinline__ real pair_dist2(const real* xs, int i, int j, int dim, int stride) {
-    real s = real(0);
-    for (int c = 0; c < dim; ++c) {
-        real df = xs[(i * dim + c) * stride] - xs[(j * dim + c) * stride];
-        s = r_fma(df, df, s);
+// Interaction cost of one sample for agents i = part, part+TPS, ... against every j > i (Cross2D.py:147-160,
+// SwarmTraj.py:147-162).  Fast path: only the minimum squared distance of my pairs is tracked (DIM loads,
+// DIM subs/fmas and one min per pair); the exact sqrt / cut-off / exp / "== 1" rule runs only when some pair is
+// within the (slightly widened) cut-off, which on the benchmark distributions is < 1 % of the evaluations.
+template <int DIM, int TSP, typename real>
+__device__ __forceinline__ real interaction_pairs(const real* xs, int A, int part, int tps, real cut, real c2) {
+    const real guard = cut * cut * real(1.0001);
+    real dmin = guard;
+    for (int i = part; i < A - 1; i += tps) {
+        real xi[DIM];
+#pragma unroll
+        for (int c = 0; c < DIM; ++c) xi[c] = xs[(i * DIM + c) * TSP];
+        const real* pj = xs + (i + 1) * DIM * TSP;
+#pragma unroll 4
+        for (int j = i + 1; j < A; ++j, pj += DIM * TSP) {
+            real d2 = real(0);
+#pragma unroll
+            for (int c = 0; c < DIM; ++c) { real df = xi[c] - pj[c * TSP]; d2 = r_fma(df, df, d2); }
+            dmin = fmin(dmin, d2);
+        }
     }
-    return s;
+    real w = real(0);
+    if (dmin < guard) {                   // rare: redo my pairs exactly
+        for (int i = part; i < A - 1; i += tps) {
+            for (int j = i + 1; j < A; ++j) {
+                real d2 = real(0);
+#pragma unroll
+                for (int c = 0; c < DIM; ++c) { real df = xs[(i * DIM + c) * TSP] - xs[(j * DIM + c) * TSP]; d2 = r_fma(df, df, d2); }
+                if (d2 < guard) {
+                    real dd = r_sqrt(d2);
+                    if (dd < cut) {
+                        real e = r_exp(-(dd * dd) / c2);
+                        if (e != real(1)) w += e;   // pairs whose Gaussian rounds to 1 are dropped (mask2)
+                    }
+                }
+            }
+        }
+    }
+    return w;
 }
 
 // Fills, for every sample of the tile, SC rows L, HJ = |Phi_t - H|, Q, W (and H in row 7), from x in
@@ -433,12 +495,13 @@ __device__ __forceinline__ real pair_dist2(const real* xs, int i, int j, int dim
 // Quadcopter.py:86-113).  Quadcopter also leaves u/mass, f7, f8, f9, u per agent in QX for the
 // dynamics and the controls.
 template <class C, typename real>
-__device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Panels<real>& tp, int tid) {
+__device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Panels& tp, int tid) {
     constexpr int TS = C::TS, TSP = C::TSP, TPS = C::TPS;
+    real* sm = smem_base<real>();
     const int s = tid % TS, part = tid / TS;
-    const real* xs = tp.S + s;
-    const real* ps = tp.G + s;
-    real* sc = tp.SC + s;
+    const real* xs = sm + tp.S + s;
+    const real* ps = sm + tp.G + s;
+    real* sc = sm + tp.SC + s;
 
     if (pr.kind == 2) {                   // ---------------- Quadcopter
         if (part == 0) {
@@ -473,7 +536,7 @@ __device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Pane
                 real xv = x[6 * TSP] * p[0] + x[7 * TSP] * p[1 * TSP] + x[8 * TSP] * p[2 * TSP];
                 real xw = x[9 * TSP] * p[3 * TSP] + x[10 * TSP] * p[4 * TSP] + x[11 * TSP] * p[5 * TSP];
                 H = H - L - xv - xw - um * fp + real(pr.grav) * p8 + real(0.5) * sq;
-                real* qx = tp.QX + (a * 5) * TSP + s;
+                real* qx = sm + tp.QX + (a * 5) * TSP + s;
                 qx[0] = um; qx[TSP] = f7; qx[2 * TSP] = f8; qx[3 * TSP] = f9; qx[4 * TSP] = u;
             }
             sc[SC_L * TSP] = L;
@@ -492,33 +555,28 @@ __device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Pane
     for (int r = part; r < d; r += TPS) { real v = ps[r * TSP]; pp = r_fma(v, v, pp); }
     const bool needQ = (pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0);
     if (needQ)
-        for (int a = part; a < A; a += TPS) q += terrain_agent<real>(pr, xs + a * dim * TSP, TSP);
+        for (int a = part; a < A; a += TPS) {
+            const real* xa = xs + a * dim * TSP;
+            q += terrain_agent<real>(pr, xa[0], xa[TSP], dim == 3 ? xa[2 * TSP] : real(0));
+        }
     if (pr.alph_W != 0.0 && A >= 2) {
         const real cut = real(pr.cutW);
         const real c2 = real(2 * pr.r * pr.r);
         if (A == 2) {                     // Cross2D.py:133-145 / SwarmTraj.py:136-145: no "== 1" rule here
             if (part == 0) {
-                real dd = r_sqrt(pair_dist2<real>(xs, 0, 1, dim, TSP));
+                real d2 = real(0);
+                for (int c = 0; c < dim; ++c) { real df = xs[c * TSP] - xs[(dim + c) * TSP]; d2 = r_fma(df, df, d2); }
+                real dd = r_sqrt(d2);
                 if (dd < cut) w = r_exp(-(dd * dd) / c2);
             }
-        } else {                          // Cross2D.py:147-160 / SwarmTraj.py:147-162
-            const real guard = cut * cut * real(1.0001);
-            for (int i = part; i < A; i += TPS) {
-                for (int j = i + 1; j < A; ++j) {
-                    real d2 = pair_dist2<real>(xs, i, j, dim, TSP);
-                    if (d2 < guard) {
-                        real dd = r_sqrt(d2);
-                        if (dd < cut) {
-                            real e = r_exp(-(dd * dd) / c2);
-                            if (e != real(1)) w += e;   // pairs whose Gaussian rounds to 1 are dropped (mask2)
-                        }
-                    }
-                }
-            }
+        } else if (dim == 2) {
+            w = interaction_pairs<2, TSP, real>(xs, A, part, TPS, cut, c2);
+        } else {
+            w = interaction_pairs<3, TSP, real>(xs, A, part, TPS, cut, c2);
         }
     }
     if (TPS > 1) {
-        real* red = tp.RED + s;
+        real* red = sm + tp.RED + s;
         red[(0 * TPS + part) * TSP] = pp;
         red[(1 * TPS + part) * TSP] = q;
         red[(2 * TPS + part) * TSP] = w;
@@ -552,72 +610,73 @@ __device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Pane
 
 // dx/dt = -grad_p H for state row `row` of sample `s` (Cross2D.py:69-70, SwarmTraj.py:68-69, Quadcopter.py:65-84)
 template <class C, typename real>
-__device__ __forceinline__ real state_rate(const ProbPack& pr, const Panels<real>& tp, int row, int s) {
+__device__ __forceinline__ real state_rate(const ProbPack& pr, const Panels& tp, int row, int s) {
     constexpr int TSP = C::TSP;
-    if (pr.kind != 2) return -tp.G[row * TSP + s];
+    const real* sm = smem_base<real>();
+    if (pr.kind != 2) return -sm[tp.G + row * TSP + s];
     int a = row / 12, c = row % 12;
-    if (c < 6) return tp.S[(a * 12 + 6 + c) * TSP + s];
+    if (c < 6) return sm[tp.S + (a * 12 + 6 + c) * TSP + s];
     if (c < 9) {
-        real um = tp.QX[(a * 5) * TSP + s];
-        real f = tp.QX[(a * 5 + 1 + (c - 6)) * TSP + s];
+        real um = sm[tp.QX + (a * 5) * TSP + s];
+        real f = sm[tp.QX + (a * 5 + 1 + (c - 6)) * TSP + s];
         real g = -um * f;
         if (c == 8) g = g + real(pr.grav);
         return -g;
     }
-    return -(real(0.5) * tp.G[row * TSP + s]);
+    return -(real(0.5) * sm[tp.G + row * TSP + s]);
 }
 
 // control channel `c` of sample `s` (calcCtrls: Cross2D.py:164-165, SwarmTraj.py:166-167, Quadcopter.py:165-174)
 template <class C, typename real>
-__device__ __forceinline__ real control_value(const ProbPack& pr, const Panels<real>& tp, int c, int s) {
+__device__ __forceinline__ real control_value(const ProbPack& pr, const Panels& tp, int c, int s) {
     constexpr int TSP = C::TSP;
-    if (pr.kind != 2) return -tp.G[c * TSP + s];
+    const real* sm = smem_base<real>();
+    if (pr.kind != 2) return -sm[tp.G + c * TSP + s];
     int a = c / 4, q = c % 4;
-    if (q == 0) return tp.QX[(a * 5 + 4) * TSP + s];
-    return real(-0.5) * tp.G[(a * 12 + 8 + q) * TSP + s];
+    if (q == 0) return sm[tp.QX + (a * 5 + 4) * TSP + s];
+    return real(-0.5) * sm[tp.G + (a * 12 + 8 + q) * TSP + s];
 }
 
 // ------------------------------------------------------------------------------------------------
 // the kernel
 // ------------------------------------------------------------------------------------------------
-template <class C, typename real>
-__device__ __forceinline__ void carve(const RolloutArgs<real>& A, real* base, Panels<real>& tp) {
+template <class C>
+__device__ __forceinline__ void carve(const SmemPlan& sp, Panels& tp) {
     constexpr int TSP = C::TSP;
-    const SmemPlan& sp = A.sp;
-    tp.U = base + sp.U * TSP; tp.U2 = base + sp.U2 * TSP;
-    for (int i = 0; i < MAXL; ++i) tp.T[i] = base + sp.T[i] * TSP;
-    tp.Zb = base + sp.Zb * TSP; tp.S = base + sp.S * TSP; tp.G = base + sp.G * TSP; tp.Qs = base + sp.Qs * TSP;
-    tp.Z0 = base + sp.Z0 * TSP; tp.ZA = base + sp.ZA * TSP; tp.SC = base + sp.SC * TSP; tp.RED = base + sp.RED * TSP;
-    tp.PN = base + sp.PN * TSP; tp.QX = base + sp.QX * TSP;
-    tp.wb = C::WSMEM ? (base + sp.wsm_off) : A.phi.blob;
+    tp.U = sp.U * TSP; tp.U2 = sp.U2 * TSP;
+    for (int i = 0; i < MAXL; ++i) tp.T[i] = sp.T[i] * TSP;
+    tp.Zb = sp.Zb * TSP; tp.S = sp.S * TSP; tp.G = sp.G * TSP; tp.Qs = sp.Qs * TSP;
+    tp.Z0 = sp.Z0 * TSP; tp.ZA = sp.ZA * TSP; tp.SC = sp.SC * TSP; tp.RED = sp.RED * TSP;
+    tp.PN = sp.PN * TSP; tp.QX = sp.QX * TSP;
+    tp.W = sp.wsm_off;
 }
 
-// S[0..d) <- src[0..d), S[d] <- t
+// S[0..d) <- panel `src`[0..d), S[d] <- t
 template <class C, typename real>
-__device__ __forceinline__ void stage_input_from(const Panels<real>& tp, const real* src, int d, real t, int tid) {
+__device__ __forceinline__ void stage_input_from(const Panels& tp, int src, int d, real t, int tid) {
     constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
+    real* sm = smem_base<real>();
     for (int idx = tid; idx < (d + 1) * TS; idx += NT) {
         int row = idx / TS, s = idx % TS;
-        tp.S[row * TSP + s] = (row < d) ? src[row * TSP + s] : t;
+        sm[tp.S + row * TSP + s] = (row < d) ? sm[src + row * TSP + s] : t;
     }
 }
 
 template <class C, typename real>
 __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> A, const int kmode) {
     constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    real* base = reinterpret_cast<real*>(smem_raw);
-    Panels<real> tp;
-    carve<C>(A, base, tp);
+    real* sm = smem_base<real>();
+    Panels tp;
+    carve<C>(A.sp, tp);
     const ThreadMap<C> tm;
     const int tid = tm.tid;
     const PhiPack<real>& P = A.phi;
     const ProbPack& pr = A.prob;
     const int d = P.d, D = P.D;
+    const int wbase = C::WSMEM ? tp.W : 0;
 
     if (C::WSMEM) {                       // stage the packed weights once per CTA
-        real* wdst = base + A.sp.wsm_off;
-        for (int i = tid; i < P.blob_len; i += NT) wdst[i] = P.blob[i];
+        for (int i = tid; i < P.blob_len; i += NT) sm[tp.W + i] = P.blob[i];
     }
     __syncthreads();
 
@@ -633,7 +692,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             for (int idx = tid; idx < TS * D; idx += NT) {
                 int s = idx / D, c = idx % D;
                 long long gs = s0 + (s < nvalid ? s : nvalid - 1);
-                tp.S[c * TSP + s] = A.x[gs * D + c];
+                sm[tp.S + c * TSP + s] = A.x[gs * D + c];
             }
             __syncthreads();
             phi_chain<C, real, true>(P, tp, tm);
@@ -641,19 +700,19 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             for (int s = tid; s < nvalid; s += NT) {
                 if (A.out_a) {
                     real phiN = real(0), quad = real(0), lin = real(0);
-                    for (int k = 0; k < C::NWO * C::WO; ++k) phiN += tp.PN[k * TSP + s];
+                    for (int k = 0; k < C::NWO * C::WO; ++k) phiN += sm[tp.PN + k * TSP + s];
                     for (int o = 0; o < D; ++o) {
-                        real sv = tp.S[o * TSP + s];
-                        quad = r_fma(sv, tp.Qs[o * TSP + s], quad);
-                        lin = r_fma(tp.wb[P.off_cw + o], sv, lin);
+                        real sv = sm[tp.S + o * TSP + s];
+                        quad = r_fma(sv, sm[tp.Qs + o * TSP + s], quad);
+                        lin = r_fma(wload<C>(P.blob, wbase + P.off_cw + o), sv, lin);
                     }
-                    A.out_a[s0 + s] = phiN + real(0.5) * quad + (lin + tp.wb[P.off_cb]);
+                    A.out_a[s0 + s] = phiN + real(0.5) * quad + (lin + wload<C>(P.blob, wbase + P.off_cb));
                 }
             }
             if (A.out_b)
                 for (int idx = tid; idx < nvalid * D; idx += NT) {
                     int s = idx / D, c = idx % D;
-                    A.out_b[(s0 + s) * D + c] = tp.G[c * TSP + s];
+                    A.out_b[(s0 + s) * D + c] = sm[tp.G + c * TSP + s];
                 }
             __syncthreads();
             continue;
@@ -662,42 +721,41 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             for (int idx = tid; idx < TS * d; idx += NT) {
                 int s = idx / d, c = idx % d;
                 long long gs = s0 + (s < nvalid ? s : nvalid - 1);
-                tp.S[c * TSP + s] = A.x[gs * d + c];
-                tp.G[c * TSP + s] = A.p_in[gs * d + c];
+                sm[tp.S + c * TSP + s] = A.x[gs * d + c];
+                sm[tp.G + c * TSP + s] = A.p_in[gs * d + c];
             }
-            for (int s = tid; s < TS; s += NT) tp.G[d * TSP + s] = real(0);
+            for (int s = tid; s < TS; s += NT) sm[tp.G + d * TSP + s] = real(0);
             __syncthreads();
-            problem_phase<C>(pr, d, tp, tid);
+            problem_phase<C, real>(pr, d, tp, tid);
             __syncthreads();
             if (A.out_a)
                 for (int s = tid; s < nvalid; s += NT) {
                     real* o = A.out_a + (s0 + s) * 4;
-                    o[0] = tp.SC[SC_L * TSP + s]; o[1] = tp.SC[7 * TSP + s];
-                    o[2] = tp.SC[SC_Q * TSP + s]; o[3] = tp.SC[SC_W * TSP + s];
+                    o[0] = sm[tp.SC + SC_L * TSP + s]; o[1] = sm[tp.SC + 7 * TSP + s];
+                    o[2] = sm[tp.SC + SC_Q * TSP + s]; o[3] = sm[tp.SC + SC_W * TSP + s];
                 }
             if (A.out_b)
                 for (int idx = tid; idx < nvalid * d; idx += NT) {
                     int s = idx / d, c = idx % d;
-                    A.out_b[(s0 + s) * d + c] = -state_rate<C>(pr, tp, c, s);
+                    A.out_b[(s0 + s) * d + c] = -state_rate<C, real>(pr, tp, c, s);
                 }
             if (A.out_c)
                 for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
                     int s = idx / pr.nctrl, c = idx % pr.nctrl;
-                    A.out_c[(s0 + s) * pr.nctrl + c] = control_value<C>(pr, tp, c, s);
+                    A.out_c[(s0 + s) * pr.nctrl + c] = control_value<C, real>(pr, tp, c, s);
                 }
             __syncthreads();
             continue;
         }
 
         // ---------------------------------------------------------------- rollout (OCflow.py:7-95)
-        real* Z0 = tp.Z0;
-        real* ZA = tp.ZA;
+        int Z0 = tp.Z0, ZA = tp.ZA;
         for (int idx = tid; idx < TS * d; idx += NT) {       // z = [x, 0, 0, 0, 0]  (OCflow.py:33)
             int s = idx / d, c = idx % d;
             long long gs = s0 + (s < nvalid ? s : nvalid - 1);   // padding samples replay the last valid one
-            Z0[c * TSP + s] = A.x[gs * d + c];
+            sm[Z0 + c * TSP + s] = A.x[gs * d + c];
         }
-        for (int idx = tid; idx < 4 * TS; idx += NT) Z0[(d + idx / TS) * TSP + idx % TS] = real(0);
+        for (int idx = tid; idx < 4 * TS; idx += NT) sm[Z0 + (d + idx / TS) * TSP + idx % TS] = real(0);
         __syncthreads();
 
         const bool inter = (A.mode == 2);
@@ -705,7 +763,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
         if (inter) {                                          // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
             for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
                 int s = idx / (d + 4), row = idx % (d + 4);
-                A.out_b[((s0 + s) * (d + 4) + row) * ntp1] = Z0[row * TSP + s];
+                A.out_b[((s0 + s) * (d + 4) + row) * ntp1] = sm[Z0 + row * TSP + s];
             }
             for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
                 int s = idx / pr.nctrl, c = idx % pr.nctrl;
@@ -718,7 +776,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             const double* tt = A.times + 5 * k;
             const real hstep = real(tt[4]);                   // h = t1 - t0 recomputed per step (OCflow.py:169)
             if (nstage > 0) {
-                stage_input_from<C>(tp, Z0, d, real(tt[0]), tid);
+                stage_input_from<C, real>(tp, Z0, d, real(tt[0]), tid);
                 tile_sync<C>();
             }
             for (int st = 0; st < nstage; ++st) {
@@ -732,47 +790,47 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 const bool lastst = (st == nstage - 1);
 
                 phi_chain<C, real, false>(P, tp, tm);        // G <- grad Phi([x_stage, t])
-                problem_phase<C>(pr, d, tp, tid);            // SC <- L, |Phi_t - H|, Q, W
+                problem_phase<C, real>(pr, d, tp, tid);            // SC <- L, |Phi_t - H|, Q, W
 
                 if (pr.kind == 2) {                           // Quadcopter rates read other rows of S: K first, then update
                     for (int idx = tid; idx < d * TS; idx += NT) {
                         int row = idx / TS, s = idx % TS;
-                        real f = state_rate<C>(pr, tp, row, s);
-                        tp.G[row * TSP + s] = hstep * f;
+                        real f = state_rate<C, real>(pr, tp, row, s);
+                        sm[tp.G + row * TSP + s] = hstep * f;
                     }
                     tile_sync<C>();
                 }
                 for (int idx = tid; idx < (d + 4) * TS; idx += NT) {
                     int row = idx / TS, s = idx % TS;
                     real kk;
-                    if (row >= d) kk = hstep * tp.SC[(row - d) * TSP + s];
-                    else if (pr.kind == 2) kk = tp.G[row * TSP + s];
-                    else kk = hstep * (-tp.G[row * TSP + s]);
-                    real z0v = Z0[row * TSP + s];
-                    real zprev = (st == 0) ? z0v : ZA[row * TSP + s];
-                    ZA[row * TSP + s] = zprev + wgt * kk;
-                    if (!lastst && row < d) tp.S[row * TSP + s] = z0v + cnext * kk;
+                    if (row >= d) kk = hstep * sm[tp.SC + (row - d) * TSP + s];
+                    else if (pr.kind == 2) kk = sm[tp.G + row * TSP + s];
+                    else kk = hstep * (-sm[tp.G + row * TSP + s]);
+                    real z0v = sm[Z0 + row * TSP + s];
+                    real zprev = (st == 0) ? z0v : sm[ZA + row * TSP + s];
+                    sm[ZA + row * TSP + s] = zprev + wgt * kk;
+                    if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v + cnext * kk;
                 }
                 if (!lastst)
-                    for (int s = tid; s < TS; s += NT) tp.S[d * TSP + s] = tnext;
+                    for (int s = tid; s < TS; s += NT) sm[tp.S + d * TSP + s] = tnext;
                 tile_sync<C>();
             }
-            if (nstage > 0) { real* t = Z0; Z0 = ZA; ZA = t; }
+            if (nstage > 0) { int t = Z0; Z0 = ZA; ZA = t; }
 
             if (inter) {                                      // OCflow.py:51-55
                 __syncthreads();
                 for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
                     int s = idx / (d + 4), row = idx % (d + 4);
-                    A.out_b[((s0 + s) * (d + 4) + row) * ntp1 + (k + 1)] = Z0[row * TSP + s];
+                    A.out_b[((s0 + s) * (d + 4) + row) * ntp1 + (k + 1)] = sm[Z0 + row * TSP + s];
                 }
-                stage_input_from<C>(tp, Z0, d, real(tt[3]), tid);   // new state, OLD time (quirk 3)
+                stage_input_from<C, real>(tp, Z0, d, real(tt[3]), tid);   // new state, OLD time (quirk 3)
                 __syncthreads();
                 phi_chain<C, real, false>(P, tp, tm);
-                if (pr.kind == 2) problem_phase<C>(pr, d, tp, tid);
+                if (pr.kind == 2) problem_phase<C, real>(pr, d, tp, tid);
                 __syncthreads();
                 for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
                     int s = idx / pr.nctrl, c = idx % pr.nctrl;
-                    A.out_c[((s0 + s) * pr.nctrl + c) * ntp1 + (k + 1)] = control_value<C>(pr, tp, c, s);
+                    A.out_c[((s0 + s) * pr.nctrl + c) * ntp1 + (k + 1)] = control_value<C, real>(pr, tp, c, s);
                 }
                 __syncthreads();
             }
@@ -780,7 +838,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
 
         // ---------------------------------------------------------------- terminal block (OCflow.py:58-90)
         __syncthreads();
-        stage_input_from<C>(tp, Z0, d, A.t_end, tid);
+        stage_input_from<C, real>(tp, Z0, d, A.t_end, tid);
         __syncthreads();
         phi_chain<C, real, true>(P, tp, tm);
         __syncthreads();
@@ -788,35 +846,35 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
         for (int s = tid; s < TS; s += NT) {
             real cG = real(0), hjg = real(0);
             for (int r = 0; r < d; ++r) {
-                real res = Z0[r * TSP + s] - xt[r];
+                real res = sm[Z0 + r * TSP + s] - xt[r];
                 cG = r_fma(res, res, cG);
-                hjg += r_abs(tp.G[r * TSP + s] - A.alph0 * res);
+                hjg += r_abs(sm[tp.G + r * TSP + s] - A.alph0 * res);
             }
             cG = real(0.5) * cG;
             real phiN = real(0), quad = real(0), lin = real(0);
-            for (int k = 0; k < C::NWO * C::WO; ++k) phiN += tp.PN[k * TSP + s];
+            for (int k = 0; k < C::NWO * C::WO; ++k) phiN += sm[tp.PN + k * TSP + s];
             for (int o = 0; o < D; ++o) {
-                real sv = tp.S[o * TSP + s];
-                quad = r_fma(sv, tp.Qs[o * TSP + s], quad);
-                lin = r_fma(tp.wb[P.off_cw + o], sv, lin);
+                real sv = sm[tp.S + o * TSP + s];
+                quad = r_fma(sv, sm[tp.Qs + o * TSP + s], quad);
+                lin = r_fma(wload<C>(P.blob, wbase + P.off_cw + o), sv, lin);
             }
-            real phi1 = phiN + real(0.5) * quad + (lin + tp.wb[P.off_cb]);
-            real* sc = tp.SC + s;
-            sc[0 * TSP] = Z0[d * TSP + s];                    // L
+            real phi1 = phiN + real(0.5) * quad + (lin + wload<C>(P.blob, wbase + P.off_cb));
+            real* sc = sm + tp.SC + s;
+            sc[0 * TSP] = sm[Z0 + d * TSP + s];               // L
             sc[1 * TSP] = cG;                                 // G
-            sc[2 * TSP] = Z0[(d + 1) * TSP + s];              // HJt
+            sc[2 * TSP] = sm[Z0 + (d + 1) * TSP + s];         // HJt
             sc[3 * TSP] = r_abs(phi1 - A.alph0 * cG);         // HJfin
             sc[4 * TSP] = hjg;                                // HJgrad
-            sc[5 * TSP] = Z0[(d + 2) * TSP + s];              // Q
-            sc[6 * TSP] = Z0[(d + 3) * TSP + s];              // W
+            sc[5 * TSP] = sm[Z0 + (d + 2) * TSP + s];         // Q
+            sc[6 * TSP] = sm[Z0 + (d + 3) * TSP + s];         // W
         }
         __syncthreads();
         if (A.mode == 0) {
-            if (tid < 7) for (int s = 0; s < nvalid; ++s) csum += (double)tp.SC[tid * TSP + s];
+            if (tid < 7) for (int s = 0; s < nvalid; ++s) csum += (double)sm[tp.SC + tid * TSP + s];
             cnt += nvalid;
         } else if (A.mode == 1) {
             for (int s = tid; s < nvalid; s += NT) {
-                const real* sc = tp.SC + s;
+                const real* sc = sm + tp.SC + s;
                 real L = sc[0], Gc = sc[TSP], HJt = sc[2 * TSP], HJf = sc[3 * TSP], HJg = sc[4 * TSP];
                 real* o = A.out_a + (s0 + s) * 8;
                 o[0] = L + A.alph0 * Gc + A.alph3 * HJt + A.alph4 * HJf + A.alph5 * HJg;   // OCflow.py:75
