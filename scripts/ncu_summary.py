@@ -1,0 +1,23 @@
+"""usage: python scripts/ncu_summary.py rep.ncu-rep  -- headline metrics + stall mix of the profiled kernel"""
+import csv, subprocess, sys
+rep = sys.argv[1]
+out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(out.splitlines()))
+hdr, vals = rows[0], rows[-1]
+m = dict(zip(hdr, vals))
+keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fmaheavy.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_fmalite.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "smsp__warps_eligible.avg.per_cycle_active",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+        "smsp__inst_executed.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
+        "smsp__inst_executed_op_global_ld.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+for k in keys:
+    if k in m:
+        print("%-70s %s" % (k, m[k]))
+st = [(float(v), k) for k, v in m.items() if "average_warp_latency_issue_stalled" in k or ("warps_issue_stalled" in k and k.endswith("_per_warp_active.pct"))]
+for v, k in sorted(st, reverse=True)[:10]:
+    print("%-70s %.3f" % (k, v))
