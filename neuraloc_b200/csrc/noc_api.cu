@@ -70,15 +70,64 @@ static __global__ void __launch_bounds__(256) fma_peak_kernel(real* out, int ite
     if (s == real(123456789)) out[blockIdx.x * blockDim.x + threadIdx.x] = s;   // keeps the loop alive
 }
 
+// Inner-loop ceiling: the register-tiled outer product of the rollout's contractions (8x8 tile per thread, both
+// operand vectors re-read from shared memory every k-step, no barriers, no epilogue) at a given residency.
+// It separates "what the FMA pipe + register file sustain for this instruction pattern" from pipeline losses.
+template <int WARPS>
+static __global__ void __launch_bounds__(32 * WARPS) fma_tile_peak_kernel(float* out, int ksteps) {
+    extern __shared__ __align__(16) unsigned char peak_smem[];
+    float* sm = reinterpret_cast<float*>(peak_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 64 * 64 * 2; i += 32 * WARPS) sm[i] = 1.0f + 1e-6f * (i & 63);
+    __syncthreads();
+    const float* W = sm + (lane & 7) * 4;             // 8 lanes x 16-byte chunks, like ld_wrow
+    const float* Ain = sm + 64 * 64 + (lane >> 3) * 8;
+    float acc[8][8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+    float w[2][8], a[2][8];
+    auto ldw = [&](int k, float (&v)[8]) {
+        float4 t0 = *reinterpret_cast<const float4*>(W + (k & 63) * 64);
+        float4 t1 = *reinterpret_cast<const float4*>(W + (k & 63) * 64 + 32);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    };
+    auto lda = [&](int k, float (&v)[8]) {
+        float4 t0 = *reinterpret_cast<const float4*>(Ain + (k & 63) * 64);
+        float4 t1 = *reinterpret_cast<const float4*>(Ain + (k & 63) * 64 + 4);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    };
+    ldw(0, w[0]); lda(0, a[0]);
+    for (int k = 0; k < ksteps; k += 2) {
+        ldw(k + 1, w[1]); lda(k + 1, a[1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[0][i], a[0][j], acc[i][j]);
+        ldw(k + 2, w[0]); lda(k + 2, a[0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(w[1][i], a[1][j], acc[i][j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s += acc[i][j];
+    if (s == 123456789.f) out[blockIdx.x * blockDim.x + tid] = s;
+}
+
 struct CfgInfo {
-    int id, PB, TS, TSP, NT, TPS, NWOxWO;
+    int id, PB, WB, NWO, TS, TSP, NT, TPS;
     bool wsmem;
     size_t elt;
     const char* name;
 };
 template <class C>
 static CfgInfo info_of(int id, const char* name) {
-    return CfgInfo{id, C::PB, C::TS, C::TSP, C::NT, C::TPS, C::NWO * C::WO, C::WSMEM, sizeof(typename C::real), name};
+    return CfgInfo{id, C::PB, C::WB, C::NWO, C::TS, C::TSP, C::NT, C::TPS, C::WSMEM, sizeof(typename C::real), name};
 }
 static const CfgInfo kCfgs[] = {
     info_of<CfgF_S4>(0, "f32/small4"), info_of<CfgF_S8>(1, "f32/small8"), info_of<CfgF_M>(2, "f32/mid"),
@@ -86,53 +135,101 @@ static const CfgInfo kCfgs[] = {
     info_of<CfgD_L>(6, "f64/large"),
 };
 
-
-// blob layout + padded widths for configuration `ci`
+// blob layout + padded widths for configuration `ci`.  The matrices are laid out in the order one grad-Phi
+// evaluation consumes them (the streamed configurations prefetch along that order).  Returns false when the
+// configuration cannot hold the net (streamed configurations are single-pass: m <= PB, ceil(D/WB) <= NWO).
 template <typename real>
-static void plan_blob(PhiPack<real>& P, const CfgInfo& ci) {
-    P.Npm = align_up(P.m, ci.PB);
-    P.Npd = align_up(P.D, ci.PB);
-    int off = 0;
+static bool plan_blob(PhiPack<real>& P, const CfgInfo& ci) {
+    if (ci.wsmem) {
+        P.Npm = align_up(P.m, ci.PB);
+        P.Npd = align_up(P.D, ci.PB);
+        P.ntile_d = 1; P.ksplit = 1;
+    } else {
+        if (P.m > ci.PB) return false;
+        P.Npm = ci.PB;
+        P.ntile_d = ceil_div(P.D, ci.WB);
+        if (P.ntile_d > ci.NWO) return false;
+        P.Npd = P.ntile_d * ci.WB;
+        // spare warps (NWO > ntile_d) take K-slices of the D-wide contractions
+        P.ksplit = std::max(1, ci.NWO / P.ntile_d);
+    }
+    int off = 0, q = 0;
     auto take = [&](int n) { int o = off; off += align_up(n, 8); return o; };
-    P.off_W1 = take(P.D * P.Npm);
+    auto seq = [&](int o, int N, int K) { P.seq_off[q] = o; P.seq_N[q] = N; P.seq_K[q] = K; ++q; };
     for (int l = 0; l < MAXL; ++l) { P.off_Kf[l] = 0; P.off_Kr[l] = 0; P.off_b[l] = 0; }
-    for (int l = 1; l < P.nTh; ++l) { P.off_Kf[l] = take(P.m * P.Npm); P.off_Kr[l] = take(P.m * P.Npm); }
-    P.off_W4 = take(P.m * P.Npd);
-    P.off_sym = take(P.D * P.Npd);
+    P.off_W1 = take(P.D * P.Npm);                  seq(P.off_W1, P.Npm, P.D);
+    for (int l = 1; l < P.nTh; ++l) { P.off_Kf[l] = take(P.m * P.Npm); seq(P.off_Kf[l], P.Npm, P.m); }
+    for (int l = P.nTh - 1; l >= 1; --l) { P.off_Kr[l] = take(P.m * P.Npm); seq(P.off_Kr[l], P.Npm, P.m); }
+    P.off_sym = take(P.D * P.Npd);                 seq(P.off_sym, P.Npd, P.D);
+    P.off_W4 = take(P.m * P.Npd);                  seq(P.off_W4, P.Npd, P.m);
+    P.nseq = q;
     for (int l = 0; l < P.nTh; ++l) P.off_b[l] = take(P.m);
     P.off_w = take(P.m);
     P.off_cw = take(P.D);
     P.off_cb = take(1);
     P.blob_len = off;
+    return true;
 }
 
-// shared-memory panel rows for configuration `ci`; returns bytes of dynamic shared memory
-static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, int d, int m, int nTh, int npm, int npd, int blob_len,
-                        int kind, int nAgents) {
-    const int D = d + 1;
-    const bool inplace = (npm == 1);
-    const bool aliasG = inplace && (npd == 1);
-    int row = 0;
-    auto take = [&](int n) { int o = row; row += n; return o; };
-    sp.U = take(std::max(m, D));
-    sp.U2 = inplace ? sp.U : take(m);
-    for (int i = 0; i < MAXL; ++i) sp.T[i] = 0;
-    sp.T[0] = take(std::max(m, D));
-    for (int i = 1; i <= nTh - 2; ++i) sp.T[i] = take(m);
-    sp.Zb = (nTh > 2) ? take(m) : 0;
-    sp.S = take(D);
-    sp.G = aliasG ? sp.U : take(D);
-    sp.Qs = sp.T[0];
-    sp.Z0 = take(d + 4);
-    sp.ZA = take(d + 4);
-    sp.SC = take(SC_ROWS);
-    sp.RED = take(3 * ci.TPS);
-    sp.PN = take(ci.NWOxWO);
-    sp.QX = (kind == NOC_PROB_QUADCOPTER) ? take(5 * nAgents) : 0;
-    sp.rows = row;
-    sp.wsm_off = align_up(row * ci.TSP, 8);
-    size_t elems = (size_t)sp.wsm_off + (ci.wsmem ? (size_t)blob_len : 0);
-    return elems * ci.elt;
+// shared-memory panel rows for configuration `ci`; returns bytes of dynamic shared memory (0 = does not fit)
+template <typename real>
+static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P, int kind, int nAgents, size_t limit) {
+    const int d = P.d, D = P.D, m = P.m, nTh = P.nTh;
+    const int npm = P.Npm / ci.PB, npd = P.Npd / ci.PB;
+    const bool inplace = ci.wsmem ? (npm == 1) : true;
+    const bool aliasG = ci.wsmem ? (inplace && npd == 1) : true;
+    SmemPlan best{};
+    size_t best_bytes = 0;
+    long best_score = -1;
+    for (int zg = 0; zg < 2; ++zg) {                 // zg = 1: augmented state in a global scratch (frees shared memory)
+        if (zg == 1 && ci.wsmem) break;
+        int row = 0;
+        auto take = [&](int n) { int o = row; row += n; return o; };
+        sp.U = take(std::max(m, D));
+        sp.U2 = inplace ? sp.U : take(m);
+        for (int i = 0; i < MAXL; ++i) sp.T[i] = 0;
+        sp.T[0] = take(std::max(m, D));
+        for (int i = 1; i <= nTh - 2; ++i) sp.T[i] = take(m);
+        sp.Zb = (nTh > 2) ? take(m) : 0;
+        sp.S = take(D);
+        sp.G = aliasG ? sp.U : take(D);
+        sp.Qs = sp.T[0];
+        sp.z_global = zg;
+        sp.Z0 = zg ? 0 : take(d + 4);
+        sp.ZA = zg ? 0 : take(d + 4);
+        sp.SC = take(SC_ROWS);
+        sp.RED = take(3 * ci.TPS);
+        sp.PN = take(ci.NWO);
+        sp.QX = (kind == NOC_PROB_QUADCOPTER) ? take(5 * nAgents) : 0;
+        // K-split partial sums: inside T[0] above the rows Qs uses when there is room (T[0] is dead by GEMM-4)
+        {
+            const int gp_rows = (!ci.wsmem && P.ksplit > 1) ? (P.ksplit - 1) * P.Npd : 0;
+            if (gp_rows == 0) sp.GP = 0;
+            else if (D + gp_rows <= std::max(m, D)) sp.GP = sp.T[0] + D;
+            else sp.GP = take(gp_rows);
+        }
+        sp.rows = row;
+        sp.wsm_off = align_up(row * ci.TSP, 8);
+        sp.ring_slab = 0; sp.ring_ns = 0;
+        size_t panel_bytes = (size_t)sp.wsm_off * ci.elt;
+        if (ci.wsmem) {
+            size_t bytes = panel_bytes + (size_t)P.blob_len * ci.elt;
+            return bytes <= limit ? bytes : 0;
+        }
+        if (panel_bytes >= limit) continue;
+        // warp-private rings: every warp streams its own WB columns, GR = 4 rows per group, ns groups deep
+        const size_t per_group = (size_t)(ci.NT / 32) * 4 * ci.WB * ci.elt;
+        int ns = (int)std::min<size_t>((limit - panel_bytes) / per_group, 8);
+        if (ns < 2) continue;
+        const int slab = 4 * ci.WB;
+        sp.ring_slab = slab; sp.ring_ns = ns;
+        // prefer the deeper ring; at equal depth keep the augmented state in shared memory
+        long score = (long)std::min(ns, 6) * 2 + (zg == 0 ? 1 : 0);
+        if (score > best_score) { best_score = score; best = sp; best_bytes = panel_bytes + (size_t)ns * per_group; }
+    }
+    if (best_score < 0) return 0;
+    sp = best;
+    return best_bytes;
 }
 
 static int g_smem_optin = -1, g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
@@ -241,23 +338,19 @@ static int fill_phi(const noc_phi_t* ph, PhiPack<real>& P, PhiRaw<real>& R) {
     return NOC_OK;
 }
 
-// choose a configuration whose panels (+ staged weights) fit in shared memory
+// choose a configuration whose panels (+ staged weights or slab ring) fit in shared memory
 template <typename real>
 static int choose(RolloutArgs<real>& A, int dtype, int kind, int nAgents, int& cfg_id, size_t& smem) {
     int rc = device_facts();
     if (rc) return rc;
-    std::vector<int> cand = candidates(dtype, A.phi.m);
-    size_t best = 0;
-    for (int id : cand) {
+    for (int id : candidates(dtype, A.phi.m)) {
         const CfgInfo& ci = kCfgs[id];
-        plan_blob(A.phi, ci);
-        smem = plan_smem(A.sp, ci, A.phi.d, A.phi.m, A.phi.nTh, A.phi.Npm / ci.PB, A.phi.Npd / ci.PB, A.phi.blob_len,
-                         kind, nAgents);
-        if (smem <= (size_t)g_smem_optin) { cfg_id = id; return NOC_OK; }
-        best = (best == 0) ? smem : std::min(best, smem);
+        if (!plan_blob(A.phi, ci)) continue;
+        smem = plan_smem(A.sp, ci, A.phi, kind, nAgents, (size_t)g_smem_optin - META_BYTES);
+        if (smem > 0) { smem += META_BYTES; cfg_id = id; return NOC_OK; }
     }
-    return fail(NOC_ERR_NOMEM, "Phi (d=%d, m=%d, nTh=%d) needs %zu B of shared memory per tile, device offers %d B",
-                A.phi.d, A.phi.m, A.phi.nTh, best, g_smem_optin);
+    return fail(NOC_ERR_NOMEM, "Phi (d=%d, m=%d, nTh=%d) does not fit any tile configuration in %d B of shared memory",
+                A.phi.d, A.phi.m, A.phi.nTh, g_smem_optin);
 }
 
 static void stage_times_host(double t0, double t1, int nt, double* tab) {
@@ -472,6 +565,30 @@ int noc_measure_fma_peak(int32_t dtype, double* tflops) {
     if (!tflops) return fail(NOC_ERR_ARG, "tflops is NULL");
     int rc = device_facts();
     if (rc) return rc;
+    if (dtype == 2 || dtype == 3) {      // inner-loop ceiling of the 8x8 register tile at 8 / 16 resident warps per SM
+        const int ksteps = 1 << 15, smem = 64 * 64 * 2 * 4;
+        void* o = nullptr;
+        NOC_CUDA(cudaMalloc(&o, (size_t)g_sm_count * 512 * 4));
+        cudaEvent_t a0, a1;
+        NOC_CUDA(cudaEventCreate(&a0));
+        NOC_CUDA(cudaEventCreate(&a1));
+        float bestms = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            NOC_CUDA(cudaEventRecord(a0));
+            if (dtype == 2) fma_tile_peak_kernel<8><<<g_sm_count, 256, smem>>>((float*)o, ksteps);
+            else fma_tile_peak_kernel<16><<<g_sm_count, 512, smem>>>((float*)o, ksteps);
+            count_launch();
+            NOC_CUDA(cudaEventRecord(a1));
+            NOC_CUDA(cudaEventSynchronize(a1));
+            float ms = 0;
+            NOC_CUDA(cudaEventElapsedTime(&ms, a0, a1));
+            if (rep > 0) bestms = std::min(bestms, ms);
+        }
+        const double thr = (dtype == 2) ? 256.0 : 512.0;
+        *tflops = 2.0 * 64 * (double)ksteps * g_sm_count * thr / (bestms * 1e-3) / 1e12;
+        cudaEventDestroy(a0); cudaEventDestroy(a1); cudaFree(o);
+        return NOC_OK;
+    }
     const int blocks = g_sm_count * 8, threads = 256, iters = (dtype == NOC_F64) ? 4096 : 16384;
     void* out = nullptr;
     NOC_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 8));

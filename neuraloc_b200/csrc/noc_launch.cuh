@@ -28,8 +28,8 @@ static inline int align_up(int a, int b) { return ceil_div(a, b) * b; }
 //                      real   RO RS WO NWO NWS wsmem
 using CfgF_S4 = Cfg<float, 4, 4, 4, 1, 4, true>;    // id 0, m <= 16 : warp-private tiles of 128 samples
 using CfgF_S8 = Cfg<float, 8, 4, 4, 1, 4, true>;    // id 1, m <= 64 : warp-private tiles of 128 samples
-using CfgF_M = Cfg<float, 8, 8, 8, 2, 4, false>;    // id 2, m ~ 128 : 128 samples, 2 warps across outputs
-using CfgF_L = Cfg<float, 8, 8, 8, 8, 1, false>;    // id 3, m ~ 512 : 32 samples, 8 warps across outputs
+using CfgF_M = Cfg<float, 8, 8, 8, 2, 4, false>;    // id 2, m <= 128: 128 samples, 2 warps across outputs, streamed weights
+using CfgF_L = Cfg<float, 8, 8, 8, 8, 1, false>;    // id 3, m <= 512: 32 samples, 8 warps across outputs, streamed weights
 using CfgD_S8 = Cfg<double, 8, 4, 4, 1, 4, true>;   // id 4
 using CfgD_M = Cfg<double, 8, 4, 8, 2, 4, false>;   // id 5
 using CfgD_L = Cfg<double, 8, 4, 8, 8, 1, false>;   // id 6
@@ -59,7 +59,13 @@ int launch_cfg(const RolloutArgs<real>& A0, const PhiRaw<real>* raw, int kmode, 
     if (grid < 1) grid = 1;
 
     real* blob = nullptr;
+    real* zscr = nullptr;
     double* partials = nullptr;
+    if (A.sp.z_global && kmode == KMODE_ROLLOUT) {
+        A.zstride = 2 * (A.phi.d + 4) * C::TSP;
+        NOC_CUDA(cudaMallocAsync((void**)&zscr, sizeof(real) * (size_t)A.zstride * grid, st));
+        A.zscratch = zscr;
+    }
     if (raw) {
         NOC_CUDA(cudaMallocAsync((void**)&blob, sizeof(real) * (size_t)A.phi.blob_len, st));
         NOC_CUDA(cudaMemsetAsync(blob, 0, sizeof(real) * (size_t)A.phi.blob_len, st));
@@ -82,6 +88,7 @@ int launch_cfg(const RolloutArgs<real>& A0, const PhiRaw<real>* raw, int kmode, 
         NOC_CUDA(cudaFreeAsync(partials, st));
     }
     if (blob) NOC_CUDA(cudaFreeAsync(blob, st));
+    if (zscr) NOC_CUDA(cudaFreeAsync(zscr, st));
     return NOC_OK;
 }
 

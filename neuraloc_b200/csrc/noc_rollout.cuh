@@ -43,7 +43,8 @@ struct Cfg {
     // fall into distinct banks ("shared-memory panels")
     static constexpr int PAD = (sizeof(real_) == 4) ? (WO_ >= 8 ? 4 : 8) : (WO_ >= 8 ? 2 : 4);
     static constexpr int TSP = TS + PAD;
-    static constexpr bool WSMEM = WSMEM_;     // weights staged in shared memory (small nets) or read through L1/L2
+    static constexpr bool WSMEM = WSMEM_;     // whole weight blob staged in shared memory (small nets) ...
+    static constexpr bool WSTREAM = !WSMEM_;  // ... or streamed slab by slab through a cp.async ring (m >= 128)
     // a warp owns all outputs of its own samples and one thread owns one sample in the problem phase:
     // tiles are warp-private and __syncwarp() replaces __syncthreads()
     static constexpr bool WARP_PRIVATE = (NWO_ == 1) && (TPS == 1);
@@ -52,14 +53,17 @@ struct Cfg {
 };
 
 // packed column of output `o` (see PhiPack): the RO outputs a thread owns are interleaved by WO in
-// output space (so that epilogue stores of neighbouring lanes hit neighbouring panel rows) but
-// contiguous in the packed weight row (so that they load as one vector).
+// output space (so that epilogue stores of neighbouring lanes hit neighbouring panel rows) and stored
+// as 16-byte chunks in the packed weight row (so that they load as vectors).
 template <class C>
 __host__ __device__ inline int pack_col(int o) {
+    constexpr int VEC = 16 / (int)sizeof(typename C::real);      // elements per 16-byte chunk
     int pass = o / C::PB, rem = o % C::PB;
     int wo = rem / C::WB, r2 = rem % C::WB;
     int ro = r2 / C::WO, lo = r2 % C::WO;
-    return pass * C::PB + wo * C::WB + lo * C::RO + ro;
+    // chunk c = ro / VEC of every lane is stored lane-contiguous: the WO lanes of a warp read one conflict-free
+    // run of WO * 16 bytes per vector load
+    return pass * C::PB + wo * C::WB + (ro / VEC) * (C::WO * VEC) + lo * VEC + (ro % VEC);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -158,6 +162,19 @@ __device__ __forceinline__ void st_panel(double* p, const double (&v)[N]) {
     for (int i = 0; i < N / 2; ++i) *reinterpret_cast<double2*>(p + 2 * i) = make_double2(v[2 * i], v[2 * i + 1]);
 }
 
+// my RO weights of one packed row: chunk c sits WO * VEC elements after chunk c-1 (see pack_col)
+template <class C, typename real>
+__device__ __forceinline__ void ld_wrow(const real* p, real (&w)[C::RO]) {
+    constexpr int VEC = 16 / (int)sizeof(real);
+#pragma unroll
+    for (int c = 0; c < C::RO / VEC; ++c) {
+        real t[VEC];
+        ld_panel<VEC>(p + c * C::WO * VEC, t);
+#pragma unroll
+        for (int e = 0; e < VEC; ++e) w[c * VEC + e] = t[e];
+    }
+}
+
 template <class C>
 __device__ __forceinline__ void tile_sync() {
     if (C::WARP_PRIVATE) __syncwarp(); else __syncthreads();
@@ -177,7 +194,7 @@ struct ThreadMap {
         lo = lane % C::WO;
         int ls = lane / C::WO;
         scol = (ws * C::WS + ls) * C::RS;          // first of my RS sample columns
-        pcol = wo * C::WB + lo * C::RO;            // first of my RO packed weight columns (within a pass)
+        pcol = wo * C::WB + lo * (16 / (int)sizeof(typename C::real));   // my first 16-byte chunk in a packed weight row (within a pass)
         orow = wo * C::WB + lo;                    // output row of ro = 0 (within a pass); ro adds ro * WO
     }
 };
@@ -186,40 +203,70 @@ struct ThreadMap {
 // pointers as `smem_base<real>() + offset` so that the compiler keeps them in the shared address space
 // (LDS/STS) even inside non-inlined functions; pointers fetched from a struct would decay to generic LD/ST.
 struct Panels {
-    int U, U2, T[MAXL], Zb, S, G, Qs, Z0, ZA, SC, RED, PN, QX;
-    int W;            // staged weight blob (WSMEM configurations)
+    int U, U2, T[MAXL], Zb, S, G, Qs, Z0, ZA, SC, RED, PN, QX, GP;
+    int W;            // staged weight blob (WSMEM configurations) / slab ring (streamed configurations)
+    int ring_slab, ring_ns;
+    unsigned smem_u32;   // shared-window address of the dynamic shared-memory base (cp.async destinations)
+};
+
+
+__device__ __forceinline__ void cp_async16(unsigned dst_smem, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {     // at most n groups still in flight
+    if (n <= 0) asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;\n" ::: "memory");
+    else asm volatile("cp.async.wait_group 2;\n" ::: "memory");
+}
+
+// position of the weight stream of one warp: next group to issue = rows [row, row+GR) of my rows of matrix `seq`
+// (element offset `src` into the blob, `step` elements between my consecutive rows, `cnt` rows in total) goes to
+// ring slot `wslot`; the next group to consume sits in slot `cslot`.  Uniform within a warp; lives in registers.
+struct WStream { int seq, row, wslot, cslot, src, step, cnt; };
+
+// Everything the device functions need to know about the call, kept at the start of dynamic shared memory: a
+// struct reached through a pointer parameter would live in local memory, and with ~220 KB of shared memory carved
+// out of the L1 every such access is an L2 round trip (round-1 profile: long-scoreboard stalls on LDL).
+constexpr int GR = 4;         // rows per cp.async group of a warp's weight stream
+constexpr int META_WARPS = 8, META_BYTES = 4096;
+template <typename real>
+struct Meta {
+    PhiPack<real> P;
+    ProbPack pr;
+    Panels tp;
+    int wtab[META_WARPS][2 * MAXL + 1][4];   // streamed configs, per warp and matrix: src offset, row step, rows, first | stride << 16
 };
 
 extern __shared__ __align__(16) unsigned char noc_smem_raw[];
 template <typename real>
-__device__ __forceinline__ real* smem_base() { return reinterpret_cast<real*>(noc_smem_raw); }
+__device__ __forceinline__ real* smem_base() { return reinterpret_cast<real*>(noc_smem_raw + META_BYTES); }
+template <typename real>
+__device__ __forceinline__ Meta<real>& meta() { return *reinterpret_cast<Meta<real>*>(noc_smem_raw); }
 
-// scalar weight read: staged copy (shared) or the global blob through the read-only path
+// ------------------------------------------------------------------------------------------------
+// contractions
+// ------------------------------------------------------------------------------------------------
 template <class C, typename real>
-__device__ __forceinline__ real wload(const real* __restrict__ gblob, int idx) {
-    if (C::WSMEM) return smem_base<real>()[idx];     // caller adds tp.W to idx
-    return __ldg(gblob + idx);
+__device__ __forceinline__ void fma_tile(real (&acc)[C::RO][C::RS], const real (&w)[C::RO], const real (&a)[C::RS]) {
+#pragma unroll
+    for (int i = 0; i < C::RO; ++i)
+#pragma unroll
+        for (int j = 0; j < C::RS; ++j) acc[i][j] = r_fma(w[i], a[j], acc[i][j]);
 }
 
-// acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS)
-// `woff` / `in_off` are element offsets: weights from the staged copy (WSMEM) or the global blob, inputs from a panel.
-// Software-pipelined in registers: weights run 4 k-steps ahead (they may come from L2), the activation panel row
-// one step ahead (shared memory), so that every FFMA block overlaps the loads of later steps.  Loads past K are
+// WSMEM configurations: acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS), weights from the staged
+// copy of the blob.  Software-pipelined in registers (weights 4 k-steps ahead, activations 1); loads past K are
 // clamped to row K-1 (valid memory, unused), the FFMA block of a step past K is skipped.
 template <class C, typename real>
-__device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], const real* __restrict__ gblob, int woff, int ldw,
-                                         int in_off, int K) {
+__device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], int woff, int ldw, int in_off, int K) {
     constexpr int PF = 4;
     const real* in = smem_base<real>() + in_off;
-    const real* W = C::WSMEM ? (smem_base<real>() + woff) : (gblob + woff);
+    const real* W = smem_base<real>() + woff;
     real wq[PF][C::RO], a[2][C::RS];
     const int kl = K - 1;
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-        const int kk = (u < kl) ? u : kl;
-        if (C::WSMEM) ld_panel<C::RO>(W + kk * ldw, wq[u]);
-        else ld_weights_global<C::RO>(W + kk * ldw, wq[u]);
-    }
+    for (int u = 0; u < PF; ++u) ld_wrow<C>(W + ((u < kl) ? u : kl) * ldw, wq[u]);
     ld_panel<C::RS>(in, a[0]);
     for (int k = 0; k < K; k += PF) {
 #pragma unroll
@@ -227,16 +274,84 @@ __device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], const real* 
             const int kk = k + u;
             const int kn = (kk + 1 < kl) ? kk + 1 : kl;
             ld_panel<C::RS>(in + kn * C::TSP, a[(u + 1) & 1]);
-            if (kk < K) {
-#pragma unroll
-                for (int i = 0; i < C::RO; ++i)
-#pragma unroll
-                    for (int j = 0; j < C::RS; ++j) acc[i][j] = r_fma(wq[u][i], a[u & 1][j], acc[i][j]);
-            }
+            if (kk < K) fma_tile<C>(acc, wq[u], a[u & 1]);
             const int kw = (kk + PF < kl) ? kk + PF : kl;
-            if (C::WSMEM) ld_panel<C::RO>(W + kw * ldw, wq[u]);
-            else ld_weights_global<C::RO>(W + kw * ldw, wq[u]);
+            ld_wrow<C>(W + kw * ldw, wq[u]);
         }
+    }
+}
+
+// ---- streamed configurations: warp-private weight streams -----------------------------------------------------
+// A warp only ever reads ITS OWN WB columns of a weight row, so every warp streams exactly those columns through a
+// private ring in shared memory: GR rows per cp.async group, ring_ns groups deep.  All hand-over is warp-local
+// (cp.async.wait_group + __syncwarp); the stream runs ahead across contraction and stage boundaries because the
+// order in which one grad-Phi evaluation consumes the matrices is fixed (PhiPack::seq_*).
+
+// load the cached descriptor of my rows of matrix ws.seq, skipping matrices I have no rows of (idle K-split warps)
+template <typename real>
+__device__ __forceinline__ void ws_load_matrix(WStream& ws, int warp) {
+    const Meta<real>& M = meta<real>();
+    while (M.wtab[warp][ws.seq][2] == 0) ws.seq = (ws.seq + 1 == M.P.nseq) ? 0 : ws.seq + 1;
+    ws.src = M.wtab[warp][ws.seq][0];
+    ws.step = M.wtab[warp][ws.seq][1];
+    ws.cnt = M.wtab[warp][ws.seq][2];
+    ws.row = 0;
+}
+
+// issue the next group of my stream (up to GR rows of one matrix) into ring slot ws.wslot
+template <class C, typename real>
+__device__ __forceinline__ void ws_issue(WStream& ws, int warp, int lane) {
+    constexpr int VEC = 16 / (int)sizeof(real), CPR = C::WB / VEC;
+    const Meta<real>& M = meta<real>();
+    const int rows = (ws.cnt - ws.row < GR) ? (ws.cnt - ws.row) : GR;
+    const real* src = M.P.blob + ws.src;
+    const int ring = M.tp.W + (warp * M.tp.ring_ns + ws.wslot) * (GR * C::WB);
+    const unsigned dst = M.tp.smem_u32 + (unsigned)(ring * (int)sizeof(real));
+    for (int idx = lane; idx < rows * CPR; idx += 32) {
+        const int r = idx / CPR, c = idx % CPR;
+        cp_async16(dst + (unsigned)((r * C::WB + c * VEC) * (int)sizeof(real)), src + r * ws.step + c * VEC);
+    }
+    cp_async_commit();
+    ws.row += rows;
+    ws.src += rows * ws.step;
+    ws.wslot = (ws.wslot + 1 == M.tp.ring_ns) ? 0 : ws.wslot + 1;
+    if (ws.row >= ws.cnt) { ws.seq = (ws.seq + 1 == M.P.nseq) ? 0 : ws.seq + 1; ws_load_matrix<real>(ws, warp); }
+}
+
+// acc += my rows of matrix `seq` (the next one in my stream) times the matching rows of the input panel
+template <class C, typename real>
+__device__ __forceinline__ void gemm_wstream(real (&acc)[C::RO][C::RS], WStream& ws, int seq, int in_off, int lo, int warp, int lane) {
+    constexpr int VEC = 16 / (int)sizeof(real);
+    const Meta<real>& M = meta<real>();
+    const int cnt = M.wtab[warp][seq][2];
+    if (cnt == 0) return;
+    const int fs = M.wtab[warp][seq][3];
+    const int first = fs & 0xffff, stride = fs >> 16;
+    const int ns = M.tp.ring_ns;
+    const real* sm = smem_base<real>();
+    const real* ring = sm + M.tp.W + warp * ns * (GR * C::WB) + lo * VEC;
+    const real* in = sm + in_off + first * C::TSP;
+    const int astep = stride * C::TSP;
+    for (int g0 = 0; g0 < cnt; g0 += GR) {
+        const int rows = (cnt - g0 < GR) ? (cnt - g0) : GR;
+        cp_async_wait_pending(ns - 2);              // my chunks of this group have landed ...
+        __syncwarp();                               // ... and so have the other lanes'
+        ws_issue<C, real>(ws, warp, lane);          // refill the slot consumed one group ago
+        const real* Wsl = ring + ws.cslot * (GR * C::WB);
+        const real* ins = in + g0 * astep;
+        real wq[2][C::RO], a[2][C::RS];
+        ld_wrow<C>(Wsl, wq[0]);
+        ld_panel<C::RS>(ins, a[0]);
+#pragma unroll
+        for (int r = 0; r < GR; ++r) {
+            if (r + 1 < GR) {
+                const int rn = (r + 1 < rows) ? r + 1 : rows - 1;
+                ld_wrow<C>(Wsl + rn * C::WB, wq[(r + 1) & 1]);
+                ld_panel<C::RS>(ins + rn * astep, a[(r + 1) & 1]);
+            }
+            if (r < rows) fma_tile<C>(acc, wq[r & 1], a[r & 1]);
+        }
+        ws.cslot = (ws.cslot + 1 == ns) ? 0 : ws.cslot + 1;
     }
 }
 
@@ -248,29 +363,46 @@ __device__ __forceinline__ void zero_acc(real (&acc)[C::RO][C::RS]) {
         for (int j = 0; j < C::RS; ++j) acc[i][j] = real(0);
 }
 
+// m-wide contraction number `seq` of the evaluation, output pass `pass`
+template <class C, typename real>
+__device__ __forceinline__ void gemm_m(real (&acc)[C::RO][C::RS], const PhiPack<real>& P, const Panels& tp, WStream& ws,
+                                       const ThreadMap<C>& tm, int seq, int pass, int in_off) {
+    if (C::WSMEM) gemm_acc<C, real>(acc, tp.W + P.seq_off[seq] + pass * C::PB + tm.pcol, P.seq_N[seq], in_off + tm.scol, P.seq_K[seq]);
+    else gemm_wstream<C, real>(acc, ws, seq, in_off + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
+}
+
+// scalar weight read (bias, w, c): staged copy or the global blob through the read-only path
+template <class C, typename real>
+__device__ __forceinline__ real wscalar(const PhiPack<real>& P, const Panels& tp, int idx) {
+    if (C::WSMEM) return smem_base<real>()[tp.W + idx];
+    return __ldg(P.blob + idx);
+}
+
 // ------------------------------------------------------------------------------------------------
 // grad Phi (and, in the TERMINAL pass, the pieces of Phi itself) for the TS samples whose s = [x,t]
 // sits in panel S.  On return panel G holds grad_s Phi (D rows).  TERMINAL additionally leaves
 // partial sums of w . u_{nTh-1} in PN and A'A s in Qs.
 // ------------------------------------------------------------------------------------------------
 template <class C, typename real, bool TERMINAL>
-__device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp, const ThreadMap<C>& tm) {
+__device__ __noinline__ WStream phi_chain(const ThreadMap<C> tm, WStream ws) {
     constexpr int RO = C::RO, RS = C::RS, TSP = C::TSP, PB = C::PB, WO = C::WO;
+    const Meta<real>& M = meta<real>();
+    const PhiPack<real>& P = M.P;
+    const Panels& tp = M.tp;
     real* sm = smem_base<real>();
-    const real* gb = P.blob;
-    const int wbase = C::WSMEM ? tp.W : 0;          // scalar weights: staged copy or global blob
-    const int npm = P.Npm / PB, npd = P.Npd / PB;
+    const int npm = C::WSTREAM ? 1 : P.Npm / PB;
     real acc[RO][RS];
+    int seq = 0;
 
     // GEMM-1: opening layer (Phi.py:114-115); keeps act(o) in U and tanh(o) in T[0]
     for (int pass = 0; pass < npm; ++pass) {
         zero_acc<C>(acc);
-        gemm_acc<C>(acc, gb, wbase + P.off_W1 + pass * PB + tm.pcol, P.Npm, tp.S + tm.scol, P.D);
+        gemm_m<C>(acc, P, tp, ws, tm, seq, pass, tp.S);
 #pragma unroll
         for (int ro = 0; ro < RO; ++ro) {
             int o = pass * PB + tm.orow + ro * WO;
             if (o < P.m) {
-                real bb = wload<C>(gb, wbase + P.off_b[0] + o);
+                real bb = wscalar<C>(P, tp, P.off_b[0] + o);
                 real uu[RS], tt[RS];
 #pragma unroll
                 for (int j = 0; j < RS; ++j) act_tanh(acc[ro][j] + bb, uu[j], tt[j]);
@@ -279,6 +411,7 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
             }
         }
     }
+    ++seq;
     tile_sync<C>();
 
     int cur = tp.U, nxt = tp.U2;
@@ -287,17 +420,17 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
     for (int j = 0; j < RS; ++j) pn[j] = real(0);
 
     // forward ResNet layers (Phi.py:118-120): u_i = u_{i-1} + h act(K_i u_{i-1} + b_i)
-    for (int i = 1; i < P.nTh; ++i) {
+    for (int i = 1; i < P.nTh; ++i, ++seq) {
         const bool last = (i == P.nTh - 1);
         for (int pass = 0; pass < npm; ++pass) {
             zero_acc<C>(acc);
-            gemm_acc<C>(acc, gb, wbase + P.off_Kf[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, cur);
             if (nxt == cur) tile_sync<C>();      // in place (single pass): every reader of `cur` is done
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
                 int o = pass * PB + tm.orow + ro * WO;
                 if (o < P.m) {
-                    real bb = wload<C>(gb, wbase + P.off_b[i] + o);
+                    real bb = wscalar<C>(P, tp, P.off_b[i] + o);
                     real out[RS];
                     if (!last) {
                         real uo[RS], tt[RS];
@@ -310,7 +443,7 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
                         }
                         st_panel<RS>(sm + tp.T[i] + o * TSP + tm.scol, tt);
                     } else {
-                        real wv = wload<C>(gb, wbase + P.off_w + o);
+                        real wv = wscalar<C>(P, tp, P.off_w + o);
                         if (TERMINAL) {          // Phi.forward needs u_{nTh-1} (Phi.py:96): accumulate w . u_last
                             real uo[RS];
                             ld_panel<RS>(sm + cur + o * TSP + tm.scol, uo);
@@ -333,14 +466,20 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
         tile_sync<C>();
         int t = cur; cur = nxt; nxt = t;
     }
-    if (TERMINAL) st_panel<RS>(sm + tp.PN + (tm.wo * WO + tm.lo) * TSP + tm.scol, pn);
+    if (TERMINAL) {                              // w . u_last: reduce over the WO lanes that share my samples
+#pragma unroll
+        for (int j = 0; j < RS; ++j)
+#pragma unroll
+            for (int off = 1; off < WO; off <<= 1) pn[j] += __shfl_xor_sync(0xffffffffu, pn[j], off);
+        if (tm.lo == 0) st_panel<RS>(sm + tp.PN + tm.wo * TSP + tm.scol, pn);
+    }
 
     // reverse sweep (Phi.py:124-131): z_i = z_{i+1} + h K_i' (tanh(a_i) * z_{i+1}), z_{nTh} = w;
     // `cur` holds y = tanh(a_i) * z_{i+1}; the epilogue forms the next y with tanh of the layer below.
-    for (int i = P.nTh - 1; i >= 1; --i) {
+    for (int i = P.nTh - 1; i >= 1; --i, ++seq) {
         for (int pass = 0; pass < npm; ++pass) {
             zero_acc<C>(acc);
-            gemm_acc<C>(acc, gb, wbase + P.off_Kr[i] + pass * PB + tm.pcol, P.Npm, cur + tm.scol, P.m);
+            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, cur);
             if (nxt == cur) tile_sync<C>();
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
@@ -348,7 +487,7 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
                 if (o < P.m) {
                     real zi[RS], tt[RS], out[RS];
                     if (i == P.nTh - 1) {
-                        real wv = wload<C>(gb, wbase + P.off_w + o);
+                        real wv = wscalar<C>(P, tp, P.off_w + o);
 #pragma unroll
                         for (int j = 0; j < RS; ++j) zi[j] = wv + P.h * acc[ro][j];
                     } else {
@@ -370,31 +509,94 @@ __device__ __noinline__ void phi_chain(const PhiPack<real>& P, const Panels& tp,
 
     // GEMM-4 (Phi.py:133-136): grad = K0' v + A'A s + c_w'.  The A'A s product is accumulated first so that
     // the terminal pass can keep it (Phi.forward's quadratic term, Phi.py:96) without a second register tile.
-    for (int pass = 0; pass < npd; ++pass) {
-        zero_acc<C>(acc);
-        gemm_acc<C>(acc, gb, wbase + P.off_sym + pass * PB + tm.pcol, P.Npd, tp.S + tm.scol, P.D);
-        if (TERMINAL) {
+    if (C::WSMEM) {
+        const int npd = P.Npd / PB;
+        for (int pass = 0; pass < npd; ++pass) {
+            zero_acc<C>(acc);
+            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, tp.S);
+            if (TERMINAL) {
+#pragma unroll
+                for (int ro = 0; ro < RO; ++ro) {
+                    int o = pass * PB + tm.orow + ro * WO;
+                    if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                }
+            }
+            gemm_m<C>(acc, P, tp, ws, tm, seq + 1, pass, cur);
+            if (tp.G == cur) tile_sync<C>();     // G aliases the hidden panel (single pass): readers are done
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
                 int o = pass * PB + tm.orow + ro * WO;
-                if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                if (o < P.D) {
+                    real cw = wscalar<C>(P, tp, P.off_cw + o);
+                    real g[RS];
+#pragma unroll
+                    for (int j = 0; j < RS; ++j) g[j] = acc[ro][j] + cw;
+                    st_panel<RS>(sm + tp.G + o * TSP + tm.scol, g);
+                }
             }
         }
-        gemm_acc<C>(acc, gb, wbase + P.off_W4 + pass * PB + tm.pcol, P.Npd, cur + tm.scol, P.m);
-        if (tp.G == cur) tile_sync<C>();     // G aliases the hidden panel (single pass): readers are done
+        tile_sync<C>();
+    } else {
+        // streamed configurations: D is much narrower than the CTA's output span, so the warps are re-tiled as
+        // ntile_d output tiles x ksplit slices of every slab's rows; slices >= 1 hand their partial sums to slice 0
+        // through panel GP.
+        const int tile_d = tm.wo % P.ntile_d, kpart = tm.wo / P.ntile_d;
+        const int orow = tile_d * C::WB + tm.lo;
+        const bool active = kpart < P.ksplit;
+        auto exchange = [&]() {                  // sum the K-slices into slice 0 (all warps call this)
+            if (P.ksplit > 1) {
+                if (active && kpart > 0) {
 #pragma unroll
-        for (int ro = 0; ro < RO; ++ro) {
-            int o = pass * PB + tm.orow + ro * WO;
-            if (o < P.D) {
-                real cw = wload<C>(gb, wbase + P.off_cw + o);
-                real g[RS];
+                    for (int ro = 0; ro < RO; ++ro)
+                        st_panel<RS>(sm + tp.GP + ((kpart - 1) * P.Npd + orow + ro * WO) * TSP + tm.scol, acc[ro]);
+                }
+                __syncthreads();
+                if (active && kpart == 0) {
+                    for (int kp = 1; kp < P.ksplit; ++kp)
 #pragma unroll
-                for (int j = 0; j < RS; ++j) g[j] = acc[ro][j] + cw;
-                st_panel<RS>(sm + tp.G + o * TSP + tm.scol, g);
+                        for (int ro = 0; ro < RO; ++ro) {
+                            real t[RS];
+                            ld_panel<RS>(sm + tp.GP + ((kp - 1) * P.Npd + orow + ro * WO) * TSP + tm.scol, t);
+#pragma unroll
+                            for (int j = 0; j < RS; ++j) acc[ro][j] += t[j];
+                        }
+                }
+            }
+        };
+        zero_acc<C>(acc);
+        gemm_wstream<C, real>(acc, ws, seq, tp.S + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
+        if (TERMINAL) {
+            exchange();
+            if (active && kpart == 0) {
+#pragma unroll
+                for (int ro = 0; ro < RO; ++ro) {
+                    int o = orow + ro * WO;
+                    if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                }
+            } else {
+                zero_acc<C>(acc);
+            }
+            __syncthreads();                     // GP is reused by the second exchange
+        }
+        gemm_wstream<C, real>(acc, ws, seq + 1, cur + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
+        exchange();
+        __syncthreads();                         // every reader of `cur` (which G may alias) and of GP is done
+        if (active && kpart == 0) {
+#pragma unroll
+            for (int ro = 0; ro < RO; ++ro) {
+                int o = orow + ro * WO;
+                if (o < P.D) {
+                    real cw = wscalar<C>(P, tp, P.off_cw + o);
+                    real g[RS];
+#pragma unroll
+                    for (int j = 0; j < RS; ++j) g[j] = acc[ro][j] + cw;
+                    st_panel<RS>(sm + tp.G + o * TSP + tm.scol, g);
+                }
             }
         }
+        __syncthreads();
     }
-    tile_sync<C>();
+    return ws;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,8 +697,11 @@ __device__ __forceinline__ real interaction_pairs(const real* xs, int A, int par
 // Quadcopter.py:86-113).  Quadcopter also leaves u/mass, f7, f8, f9, u per agent in QX for the
 // dynamics and the controls.
 template <class C, typename real>
-__device__ __noinline__ void problem_phase(const ProbPack& pr, int d, const Panels& tp, int tid) {
+__device__ __noinline__ void problem_phase(int d, int tid) {
     constexpr int TS = C::TS, TSP = C::TSP, TPS = C::TPS;
+    const Meta<real>& M = meta<real>();
+    const ProbPack& pr = M.pr;
+    const Panels& tp = M.tp;
     real* sm = smem_base<real>();
     const int s = tid % TS, part = tid / TS;
     const real* xs = sm + tp.S + s;
@@ -647,18 +852,19 @@ __device__ __forceinline__ void carve(const SmemPlan& sp, Panels& tp) {
     for (int i = 0; i < MAXL; ++i) tp.T[i] = sp.T[i] * TSP;
     tp.Zb = sp.Zb * TSP; tp.S = sp.S * TSP; tp.G = sp.G * TSP; tp.Qs = sp.Qs * TSP;
     tp.Z0 = sp.Z0 * TSP; tp.ZA = sp.ZA * TSP; tp.SC = sp.SC * TSP; tp.RED = sp.RED * TSP;
-    tp.PN = sp.PN * TSP; tp.QX = sp.QX * TSP;
-    tp.W = sp.wsm_off;
+    tp.PN = sp.PN * TSP; tp.QX = sp.QX * TSP; tp.GP = sp.GP * TSP;
+    tp.W = sp.wsm_off; tp.ring_slab = sp.ring_slab; tp.ring_ns = sp.ring_ns;
+    tp.smem_u32 = (unsigned)__cvta_generic_to_shared(noc_smem_raw + META_BYTES);   // = smem_base()
 }
 
-// S[0..d) <- panel `src`[0..d), S[d] <- t
+// S[0..d) <- rows of `src` (a [row][TSP] panel in shared memory or in the global scratch), S[d] <- t
 template <class C, typename real>
-__device__ __forceinline__ void stage_input_from(const Panels& tp, int src, int d, real t, int tid) {
+__device__ __forceinline__ void stage_input_from(const Panels& tp, const real* src, int d, real t, int tid) {
     constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
     real* sm = smem_base<real>();
     for (int idx = tid; idx < (d + 1) * TS; idx += NT) {
         int row = idx / TS, s = idx % TS;
-        sm[tp.S + row * TSP + s] = (row < d) ? sm[src + row * TSP + s] : t;
+        sm[tp.S + row * TSP + s] = (row < d) ? src[row * TSP + s] : t;
     }
 }
 
@@ -666,19 +872,48 @@ template <class C, typename real>
 __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> A, const int kmode) {
     constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
     real* sm = smem_base<real>();
-    Panels tp;
-    carve<C>(A.sp, tp);
+    static_assert(sizeof(Meta<real>) <= META_BYTES, "Meta must fit in its reserved shared-memory header");
+    static_assert(C::NT / 32 <= META_WARPS, "wtab holds META_WARPS warps");
+    Meta<real>& M = meta<real>();
     const ThreadMap<C> tm;
     const int tid = tm.tid;
-    const PhiPack<real>& P = A.phi;
-    const ProbPack& pr = A.prob;
-    const int d = P.d, D = P.D;
-    const int wbase = C::WSMEM ? tp.W : 0;
-
-    if (C::WSMEM) {                       // stage the packed weights once per CTA
-        for (int i = tid; i < P.blob_len; i += NT) sm[tp.W + i] = P.blob[i];
+    if (tid == 0) {
+        M.P = A.phi;
+        M.pr = A.prob;
+        carve<C>(A.sp, M.tp);
     }
     __syncthreads();
+    const PhiPack<real>& P = M.P;
+    const ProbPack& pr = M.pr;
+    const Panels& tp = M.tp;
+    const int d = P.d, D = P.D;
+
+    WStream ws = {0, 0, 0, 0, 0, 0, 0};
+    if (C::WSMEM) {                       // stage the packed weights once per CTA
+        for (int i = tid; i < P.blob_len; i += NT) sm[tp.W + i] = P.blob[i];
+    } else {
+        // my rows of every matrix of the stream: m-wide matrices -> all rows of my WB columns; D-wide matrices ->
+        // rows kpart, kpart + ksplit, ... of output tile tile_d (or none, for warps beyond ntile_d * ksplit)
+        const int warp = tid >> 5, lane = tid & 31;
+        const int tile_d = tm.wo % P.ntile_d, kpart = tm.wo / P.ntile_d;
+        for (int q = lane; q < P.nseq; q += 32) {
+            const bool dwide = q >= P.nseq - 2;
+            const int first = dwide ? kpart : 0, stride = dwide ? P.ksplit : 1;
+            const int cnt = (dwide && kpart >= P.ksplit) ? 0 : (P.seq_K[q] - first + stride - 1) / stride;
+            M.wtab[warp][q][0] = P.seq_off[q] + first * P.seq_N[q] + (dwide ? tile_d : tm.wo) * C::WB;
+            M.wtab[warp][q][1] = stride * P.seq_N[q];
+            M.wtab[warp][q][2] = cnt > 0 ? cnt : 0;
+            M.wtab[warp][q][3] = first | (stride << 16);
+        }
+        __syncwarp();
+        if (kmode != KMODE_PROB) {        // start my weight stream: ring_ns - 1 groups in flight
+            ws_load_matrix<real>(ws, warp);
+            for (int i = 0; i < tp.ring_ns - 1; ++i) ws_issue<C, real>(ws, warp, lane);
+        }
+    }
+    __syncthreads();
+    // augmented state panels: shared memory, or this CTA's slice of the global scratch (large nets)
+    real* zb = (C::WSTREAM && A.sp.z_global) ? (A.zscratch + (size_t)blockIdx.x * A.zstride) : sm;
 
     double csum = 0.0;                    // threads 0..6: this CTA's running sum of cost q (mean mode)
     long long cnt = 0;
@@ -695,18 +930,18 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 sm[tp.S + c * TSP + s] = A.x[gs * D + c];
             }
             __syncthreads();
-            phi_chain<C, real, true>(P, tp, tm);
+            ws = phi_chain<C, real, true>(tm, ws);
             __syncthreads();
             for (int s = tid; s < nvalid; s += NT) {
                 if (A.out_a) {
                     real phiN = real(0), quad = real(0), lin = real(0);
-                    for (int k = 0; k < C::NWO * C::WO; ++k) phiN += sm[tp.PN + k * TSP + s];
+                    for (int k = 0; k < C::NWO; ++k) phiN += sm[tp.PN + k * TSP + s];
                     for (int o = 0; o < D; ++o) {
                         real sv = sm[tp.S + o * TSP + s];
                         quad = r_fma(sv, sm[tp.Qs + o * TSP + s], quad);
-                        lin = r_fma(wload<C>(P.blob, wbase + P.off_cw + o), sv, lin);
+                        lin = r_fma(wscalar<C>(P, tp, P.off_cw + o), sv, lin);
                     }
-                    A.out_a[s0 + s] = phiN + real(0.5) * quad + (lin + wload<C>(P.blob, wbase + P.off_cb));
+                    A.out_a[s0 + s] = phiN + real(0.5) * quad + (lin + wscalar<C>(P, tp, P.off_cb));
                 }
             }
             if (A.out_b)
@@ -726,7 +961,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             }
             for (int s = tid; s < TS; s += NT) sm[tp.G + d * TSP + s] = real(0);
             __syncthreads();
-            problem_phase<C, real>(pr, d, tp, tid);
+            problem_phase<C, real>(d, tid);
             __syncthreads();
             if (A.out_a)
                 for (int s = tid; s < nvalid; s += NT) {
@@ -750,12 +985,13 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
 
         // ---------------------------------------------------------------- rollout (OCflow.py:7-95)
         int Z0 = tp.Z0, ZA = tp.ZA;
+        if (C::WSTREAM && A.sp.z_global) { Z0 = 0; ZA = (d + 4) * TSP; }
         for (int idx = tid; idx < TS * d; idx += NT) {       // z = [x, 0, 0, 0, 0]  (OCflow.py:33)
             int s = idx / d, c = idx % d;
             long long gs = s0 + (s < nvalid ? s : nvalid - 1);   // padding samples replay the last valid one
-            sm[Z0 + c * TSP + s] = A.x[gs * d + c];
+            zb[Z0 + c * TSP + s] = A.x[gs * d + c];
         }
-        for (int idx = tid; idx < 4 * TS; idx += NT) sm[Z0 + (d + idx / TS) * TSP + idx % TS] = real(0);
+        for (int idx = tid; idx < 4 * TS; idx += NT) zb[Z0 + (d + idx / TS) * TSP + idx % TS] = real(0);
         __syncthreads();
 
         const bool inter = (A.mode == 2);
@@ -763,7 +999,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
         if (inter) {                                          // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
             for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
                 int s = idx / (d + 4), row = idx % (d + 4);
-                A.out_b[((s0 + s) * (d + 4) + row) * ntp1] = sm[Z0 + row * TSP + s];
+                A.out_b[((s0 + s) * (d + 4) + row) * ntp1] = zb[Z0 + row * TSP + s];
             }
             for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
                 int s = idx / pr.nctrl, c = idx % pr.nctrl;
@@ -776,7 +1012,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
             const double* tt = A.times + 5 * k;
             const real hstep = real(tt[4]);                   // h = t1 - t0 recomputed per step (OCflow.py:169)
             if (nstage > 0) {
-                stage_input_from<C, real>(tp, Z0, d, real(tt[0]), tid);
+                stage_input_from<C, real>(tp, zb + Z0, d, real(tt[0]), tid);
                 tile_sync<C>();
             }
             for (int st = 0; st < nstage; ++st) {
@@ -789,8 +1025,8 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 else { wgt = real(1.0 / 6.0); cnext = real(0); tnext = real(0); }
                 const bool lastst = (st == nstage - 1);
 
-                phi_chain<C, real, false>(P, tp, tm);        // G <- grad Phi([x_stage, t])
-                problem_phase<C, real>(pr, d, tp, tid);            // SC <- L, |Phi_t - H|, Q, W
+                ws = phi_chain<C, real, false>(tm, ws);        // G <- grad Phi([x_stage, t])
+                problem_phase<C, real>(d, tid);            // SC <- L, |Phi_t - H|, Q, W
 
                 if (pr.kind == 2) {                           // Quadcopter rates read other rows of S: K first, then update
                     for (int idx = tid; idx < d * TS; idx += NT) {
@@ -806,9 +1042,9 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                     if (row >= d) kk = hstep * sm[tp.SC + (row - d) * TSP + s];
                     else if (pr.kind == 2) kk = sm[tp.G + row * TSP + s];
                     else kk = hstep * (-sm[tp.G + row * TSP + s]);
-                    real z0v = sm[Z0 + row * TSP + s];
-                    real zprev = (st == 0) ? z0v : sm[ZA + row * TSP + s];
-                    sm[ZA + row * TSP + s] = zprev + wgt * kk;
+                    real z0v = zb[Z0 + row * TSP + s];
+                    real zprev = (st == 0) ? z0v : zb[ZA + row * TSP + s];
+                    zb[ZA + row * TSP + s] = zprev + wgt * kk;
                     if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v + cnext * kk;
                 }
                 if (!lastst)
@@ -821,12 +1057,12 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 __syncthreads();
                 for (int idx = tid; idx < nvalid * (d + 4); idx += NT) {
                     int s = idx / (d + 4), row = idx % (d + 4);
-                    A.out_b[((s0 + s) * (d + 4) + row) * ntp1 + (k + 1)] = sm[Z0 + row * TSP + s];
+                    A.out_b[((s0 + s) * (d + 4) + row) * ntp1 + (k + 1)] = zb[Z0 + row * TSP + s];
                 }
-                stage_input_from<C, real>(tp, Z0, d, real(tt[3]), tid);   // new state, OLD time (quirk 3)
+                stage_input_from<C, real>(tp, zb + Z0, d, real(tt[3]), tid);   // new state, OLD time (quirk 3)
                 __syncthreads();
-                phi_chain<C, real, false>(P, tp, tm);
-                if (pr.kind == 2) problem_phase<C, real>(pr, d, tp, tid);
+                ws = phi_chain<C, real, false>(tm, ws);
+                if (pr.kind == 2) problem_phase<C, real>(d, tid);
                 __syncthreads();
                 for (int idx = tid; idx < nvalid * pr.nctrl; idx += NT) {
                     int s = idx / pr.nctrl, c = idx % pr.nctrl;
@@ -838,35 +1074,35 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
 
         // ---------------------------------------------------------------- terminal block (OCflow.py:58-90)
         __syncthreads();
-        stage_input_from<C, real>(tp, Z0, d, A.t_end, tid);
+        stage_input_from<C, real>(tp, zb + Z0, d, A.t_end, tid);
         __syncthreads();
-        phi_chain<C, real, true>(P, tp, tm);
+        ws = phi_chain<C, real, true>(tm, ws);
         __syncthreads();
         const real* xt = static_cast<const real*>(pr.xtarget);
         for (int s = tid; s < TS; s += NT) {
             real cG = real(0), hjg = real(0);
             for (int r = 0; r < d; ++r) {
-                real res = sm[Z0 + r * TSP + s] - xt[r];
+                real res = zb[Z0 + r * TSP + s] - xt[r];
                 cG = r_fma(res, res, cG);
                 hjg += r_abs(sm[tp.G + r * TSP + s] - A.alph0 * res);
             }
             cG = real(0.5) * cG;
             real phiN = real(0), quad = real(0), lin = real(0);
-            for (int k = 0; k < C::NWO * C::WO; ++k) phiN += sm[tp.PN + k * TSP + s];
+            for (int k = 0; k < C::NWO; ++k) phiN += sm[tp.PN + k * TSP + s];
             for (int o = 0; o < D; ++o) {
                 real sv = sm[tp.S + o * TSP + s];
                 quad = r_fma(sv, sm[tp.Qs + o * TSP + s], quad);
-                lin = r_fma(wload<C>(P.blob, wbase + P.off_cw + o), sv, lin);
+                lin = r_fma(wscalar<C>(P, tp, P.off_cw + o), sv, lin);
             }
-            real phi1 = phiN + real(0.5) * quad + (lin + wload<C>(P.blob, wbase + P.off_cb));
+            real phi1 = phiN + real(0.5) * quad + (lin + wscalar<C>(P, tp, P.off_cb));
             real* sc = sm + tp.SC + s;
-            sc[0 * TSP] = sm[Z0 + d * TSP + s];               // L
+            sc[0 * TSP] = zb[Z0 + d * TSP + s];               // L
             sc[1 * TSP] = cG;                                 // G
-            sc[2 * TSP] = sm[Z0 + (d + 1) * TSP + s];         // HJt
+            sc[2 * TSP] = zb[Z0 + (d + 1) * TSP + s];         // HJt
             sc[3 * TSP] = r_abs(phi1 - A.alph0 * cG);         // HJfin
             sc[4 * TSP] = hjg;                                // HJgrad
-            sc[5 * TSP] = sm[Z0 + (d + 2) * TSP + s];         // Q
-            sc[6 * TSP] = sm[Z0 + (d + 3) * TSP + s];         // W
+            sc[5 * TSP] = zb[Z0 + (d + 2) * TSP + s];         // Q
+            sc[6 * TSP] = zb[Z0 + (d + 3) * TSP + s];         // W
         }
         __syncthreads();
         if (A.mode == 0) {
@@ -884,6 +1120,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
         __syncthreads();
     }
 
+    if (C::WSTREAM) cp_async_wait_pending(0);     // prefetched slabs nobody will consume
     if (kmode == KMODE_ROLLOUT && A.mode == 0 && A.partials) {
         if (tid < 7) A.partials[blockIdx.x * 8 + tid] = csum;
         if (tid == 7) A.partials[blockIdx.x * 8 + 7] = (double)cnt;

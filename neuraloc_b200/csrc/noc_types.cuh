@@ -27,6 +27,12 @@ struct PhiPack {
     int off_b[MAXL];           // [m] each
     int off_w, off_cw, off_cb; // [m], [D], [1]
     int blob_len;
+    // The weight matrices in the order one grad-Phi evaluation consumes them (W1, Kf_1.., Kr_nTh-1..1, sym, W4):
+    // they are laid out contiguously in that order, so a streamed configuration prefetches "the next slab" without
+    // caring about matrix boundaries (noc_rollout.cuh: WStream).
+    int nseq;
+    int seq_off[2 * MAXL + 1], seq_N[2 * MAXL + 1], seq_K[2 * MAXL + 1];
+    int ntile_d, ksplit;       // D-wide contractions (sym, W4) in streamed configs: warp tiles across outputs x K-split
 };
 
 // Raw (reference-layout) pointers handed to the pack kernel.
@@ -57,8 +63,11 @@ struct SmemPlan {
     int RED;                   // [3][TPS] partial sums of the problem phase
     int PN;                    // [NWO*WO] partial sums of w . u_last (terminal pass)
     int QX;                    // Quadcopter per-agent scalars [5 * nAgents]: u/mass, f7, f8, f9, u
+    int GP;                    // partial sums of the K-split D-wide contractions (streamed configs)
     int rows;                  // total rows
-    int wsm_off;               // element offset of the weight blob copy (WSMEM configs), after the rows
+    int wsm_off;               // element offset of the weight blob copy (WSMEM configs) / of the slab ring (streamed)
+    int ring_slab, ring_ns;    // streamed configs: elements per ring slot, number of slots (2..4)
+    int z_global;              // Z0/ZA live in a per-CTA global scratch instead of shared memory
 };
 
 constexpr int SC_L = 0, SC_HJ = 1, SC_Q = 2, SC_W = 3, SC_G = 4, SC_HJF = 5, SC_HJG = 6, SC_ROWS = 8;
@@ -79,6 +88,8 @@ struct RolloutArgs {
     real* out_a;               // noMean: [n,8]; phi-eval: phi [n];  prob-eval: lhqw [n,4]
     real* out_b;               // intermediates: zFull; phi-eval: grad [n,D]; prob-eval: gradpH [n,d]
     real* out_c;               // intermediates: ctrlFull; prob-eval: ctrls [n,nctrl]
+    real* zscratch;            // per-CTA [2][(d+4)][TSP] augmented-state scratch when sp.z_global
+    int zstride;               // elements per CTA in zscratch
     int ntiles;
 };
 
