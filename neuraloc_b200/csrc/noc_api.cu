@@ -120,14 +120,14 @@ static __global__ void __launch_bounds__(32 * WARPS) fma_tile_peak_kernel(float*
 }
 
 struct CfgInfo {
-    int id, PB, WB, NWO, TS, TSP, NT, TPS;
+    int id, PB, WB, NWO, TS, TSP, NT, TPS, GRP;
     bool wsmem;
     size_t elt;
     const char* name;
 };
 template <class C>
 static CfgInfo info_of(int id, const char* name) {
-    return CfgInfo{id, C::PB, C::WB, C::NWO, C::TS, C::TSP, C::NT, C::TPS, C::WSMEM, sizeof(typename C::real), name};
+    return CfgInfo{id, C::PB, C::WB, C::NWO, C::TS, C::TSP, C::NT, C::TPS, C::GRP, C::WSMEM, sizeof(typename C::real), name};
 }
 static const CfgInfo kCfgs[] = {
     info_of<CfgF_S4>(0, "f32/small4"), info_of<CfgF_S8>(1, "f32/small8"), info_of<CfgF_M>(2, "f32/mid"),
@@ -217,11 +217,11 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
             return bytes <= limit ? bytes : 0;
         }
         if (panel_bytes >= limit) continue;
-        // warp-private rings: every warp streams its own WB columns, GR = 4 rows per group, ns groups deep
-        const size_t per_group = (size_t)(ci.NT / 32) * 4 * ci.WB * ci.elt;
+        // warp-private rings: every warp streams its own WB columns, GRP rows per group, ns groups deep
+        const size_t per_group = (size_t)(ci.NT / 32) * ci.GRP * ci.WB * ci.elt;
         int ns = (int)std::min<size_t>((limit - panel_bytes) / per_group, 8);
         if (ns < 2) continue;
-        const int slab = 4 * ci.WB;
+        const int slab = ci.GRP * ci.WB;
         sp.ring_slab = slab; sp.ring_ns = ns;
         // prefer the deeper ring; at equal depth keep the augmented state in shared memory
         long score = (long)std::min(ns, 6) * 2 + (zg == 0 ? 1 : 0);

@@ -44,7 +44,8 @@ struct Cfg {
     static constexpr int PAD = (sizeof(real_) == 4) ? (WO_ >= 8 ? 4 : 8) : (WO_ >= 8 ? 2 : 4);
     static constexpr int TSP = TS + PAD;
     static constexpr bool WSMEM = WSMEM_;     // whole weight blob staged in shared memory (small nets) ...
-    static constexpr bool WSTREAM = !WSMEM_;  // ... or streamed slab by slab through a cp.async ring (m >= 128)
+    static constexpr bool WSTREAM = !WSMEM_;  // ... or streamed through warp-private cp.async rings (m >= 128)
+    static constexpr int GRP = (sizeof(real_) == 4) ? 8 : 4;   // rows per cp.async group of a warp's weight stream
     // a warp owns all outputs of its own samples and one thread owns one sample in the problem phase:
     // tiles are warp-private and __syncwarp() replaces __syncthreads()
     static constexpr bool WARP_PRIVATE = (NWO_ == 1) && (TPS == 1);
@@ -228,7 +229,6 @@ struct WStream { int seq, row, wslot, cslot, src, step, cnt; };
 // Everything the device functions need to know about the call, kept at the start of dynamic shared memory: a
 // struct reached through a pointer parameter would live in local memory, and with ~220 KB of shared memory carved
 // out of the L1 every such access is an L2 round trip (round-1 profile: long-scoreboard stalls on LDL).
-constexpr int GR = 4;         // rows per cp.async group of a warp's weight stream
 constexpr int META_WARPS = 8, META_BYTES = 4096;
 template <typename real>
 struct Meta {
@@ -298,18 +298,24 @@ __device__ __forceinline__ void ws_load_matrix(WStream& ws, int warp) {
     ws.row = 0;
 }
 
-// issue the next group of my stream (up to GR rows of one matrix) into ring slot ws.wslot
+// issue the next group of my stream (up to GRP rows of one matrix) into ring slot ws.wslot
 template <class C, typename real>
 __device__ __forceinline__ void ws_issue(WStream& ws, int warp, int lane) {
-    constexpr int VEC = 16 / (int)sizeof(real), CPR = C::WB / VEC;
+    constexpr int VEC = 16 / (int)sizeof(real), CPR = C::WB / VEC, GR = C::GRP;
+    constexpr int RPI = 32 / CPR;                    // rows one warp-wide cp.async covers
     const Meta<real>& M = meta<real>();
     const int rows = (ws.cnt - ws.row < GR) ? (ws.cnt - ws.row) : GR;
-    const real* src = M.P.blob + ws.src;
+    const int lr = lane / CPR, lc = (lane % CPR) * VEC;
+    const real* src = M.P.blob + ws.src + lr * ws.step + lc;
     const int ring = M.tp.W + (warp * M.tp.ring_ns + ws.wslot) * (GR * C::WB);
-    const unsigned dst = M.tp.smem_u32 + (unsigned)(ring * (int)sizeof(real));
-    for (int idx = lane; idx < rows * CPR; idx += 32) {
-        const int r = idx / CPR, c = idx % CPR;
-        cp_async16(dst + (unsigned)((r * C::WB + c * VEC) * (int)sizeof(real)), src + r * ws.step + c * VEC);
+    const unsigned dst = M.tp.smem_u32 + (unsigned)((ring + lr * C::WB + lc) * (int)sizeof(real));
+    if (rows == GR) {
+#pragma unroll
+        for (int j = 0; j < GR / RPI; ++j)
+            cp_async16(dst + (unsigned)(j * RPI * C::WB * (int)sizeof(real)), src + j * RPI * ws.step);
+    } else {
+        for (int r = lr; r < rows; r += RPI)
+            cp_async16(dst + (unsigned)((r - lr) * C::WB * (int)sizeof(real)), src + (r - lr) * ws.step);
     }
     cp_async_commit();
     ws.row += rows;
@@ -321,7 +327,7 @@ __device__ __forceinline__ void ws_issue(WStream& ws, int warp, int lane) {
 // acc += my rows of matrix `seq` (the next one in my stream) times the matching rows of the input panel
 template <class C, typename real>
 __device__ __forceinline__ void gemm_wstream(real (&acc)[C::RO][C::RS], WStream& ws, int seq, int in_off, int lo, int warp, int lane) {
-    constexpr int VEC = 16 / (int)sizeof(real);
+    constexpr int VEC = 16 / (int)sizeof(real), GR = C::GRP;
     const Meta<real>& M = meta<real>();
     const int cnt = M.wtab[warp][seq][2];
     if (cnt == 0) return;
@@ -330,26 +336,32 @@ __device__ __forceinline__ void gemm_wstream(real (&acc)[C::RO][C::RS], WStream&
     const int ns = M.tp.ring_ns;
     const real* sm = smem_base<real>();
     const real* ring = sm + M.tp.W + warp * ns * (GR * C::WB) + lo * VEC;
-    const real* in = sm + in_off + first * C::TSP;
+    const real* ins = sm + in_off + first * C::TSP;
     const int astep = stride * C::TSP;
-    for (int g0 = 0; g0 < cnt; g0 += GR) {
+    for (int g0 = 0; g0 < cnt; g0 += GR, ins += GR * astep) {
         const int rows = (cnt - g0 < GR) ? (cnt - g0) : GR;
         cp_async_wait_pending(ns - 2);              // my chunks of this group have landed ...
         __syncwarp();                               // ... and so have the other lanes'
         ws_issue<C, real>(ws, warp, lane);          // refill the slot consumed one group ago
         const real* Wsl = ring + ws.cslot * (GR * C::WB);
-        const real* ins = in + g0 * astep;
         real wq[2][C::RO], a[2][C::RS];
         ld_wrow<C>(Wsl, wq[0]);
         ld_panel<C::RS>(ins, a[0]);
+        if (rows == GR) {                           // full group: straight-line, register double-buffered
 #pragma unroll
-        for (int r = 0; r < GR; ++r) {
-            if (r + 1 < GR) {
-                const int rn = (r + 1 < rows) ? r + 1 : rows - 1;
-                ld_wrow<C>(Wsl + rn * C::WB, wq[(r + 1) & 1]);
-                ld_panel<C::RS>(ins + rn * astep, a[(r + 1) & 1]);
+            for (int r = 0; r < GR; ++r) {
+                if (r + 1 < GR) {
+                    ld_wrow<C>(Wsl + (r + 1) * C::WB, wq[(r + 1) & 1]);
+                    ld_panel<C::RS>(ins + (r + 1) * astep, a[(r + 1) & 1]);
+                }
+                fma_tile<C>(acc, wq[r & 1], a[r & 1]);
             }
-            if (r < rows) fma_tile<C>(acc, wq[r & 1], a[r & 1]);
+        } else {                                    // last group of a matrix
+            for (int r = 0; r < rows; ++r) {
+                ld_wrow<C>(Wsl + r * C::WB, wq[0]);
+                ld_panel<C::RS>(ins + r * astep, a[0]);
+                fma_tile<C>(acc, wq[0], a[0]);
+            }
         }
         ws.cslot = (ws.cslot + 1 == ns) ? 0 : ws.cslot + 1;
     }
