@@ -151,7 +151,7 @@ static bool plan_blob(PhiPack<real>& P, const CfgInfo& ci) {
         if (P.ntile_d > ci.NWO) return false;
         P.Npd = P.ntile_d * ci.WB;
         // spare warps (NWO > ntile_d) take K-slices of the D-wide contractions
-        P.ksplit = std::max(1, ci.NWO / P.ntile_d);
+        P.ksplit = ceil_div(ci.NWO, P.ntile_d);                 // most K-slices any output tile gets
     }
     int off = 0, q = 0;
     auto take = [&](int n) { int o = off; off += align_up(n, 8); return o; };
@@ -203,7 +203,7 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
         sp.QX = (kind == NOC_PROB_QUADCOPTER) ? take(5 * nAgents) : 0;
         // K-split partial sums: inside T[0] above the rows Qs uses when there is room (T[0] is dead by GEMM-4)
         {
-            const int gp_rows = (!ci.wsmem && P.ksplit > 1) ? (P.ksplit - 1) * P.Npd : 0;
+            const int gp_rows = (!ci.wsmem && P.ksplit > 1) ? P.Npd : 0;      // one K-slice is exchanged per round
             if (gp_rows == 0) sp.GP = 0;
             else if (D + gp_rows <= std::max(m, D)) sp.GP = sp.T[0] + D;
             else sp.GP = take(gp_rows);

@@ -554,27 +554,27 @@ __device__ __noinline__ WStream phi_chain(const ThreadMap<C> tm, WStream ws) {
         // through panel GP.
         const int tile_d = tm.wo % P.ntile_d, kpart = tm.wo / P.ntile_d;
         const int orow = tile_d * C::WB + tm.lo;
-        const bool active = kpart < P.ksplit;
-        auto exchange = [&]() {                  // sum the K-slices into slice 0 (all warps call this)
-            if (P.ksplit > 1) {
-                if (active && kpart > 0) {
+        const int ks_t = (C::NWO - tile_d + P.ntile_d - 1) / P.ntile_d;      // K-slices of my output tile
+        auto exchange = [&]() {                  // sum the K-slices into slice 0, one slice per round (all warps call this)
+            for (int round = 1; round < P.ksplit; ++round) {
+                if (kpart == round) {
 #pragma unroll
-                    for (int ro = 0; ro < RO; ++ro)
-                        st_panel<RS>(sm + tp.GP + ((kpart - 1) * P.Npd + orow + ro * WO) * TSP + tm.scol, acc[ro]);
+                    for (int ro = 0; ro < RO; ++ro) st_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, acc[ro]);
                 }
                 __syncthreads();
-                if (active && kpart == 0) {
-                    for (int kp = 1; kp < P.ksplit; ++kp)
+                if (kpart == 0 && round < ks_t) {
 #pragma unroll
-                        for (int ro = 0; ro < RO; ++ro) {
-                            real t[RS];
-                            ld_panel<RS>(sm + tp.GP + ((kp - 1) * P.Npd + orow + ro * WO) * TSP + tm.scol, t);
+                    for (int ro = 0; ro < RO; ++ro) {
+                        real t[RS];
+                        ld_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, t);
 #pragma unroll
-                            for (int j = 0; j < RS; ++j) acc[ro][j] += t[j];
-                        }
+                        for (int j = 0; j < RS; ++j) acc[ro][j] += t[j];
+                    }
                 }
+                if (round + 1 < P.ksplit) __syncthreads();
             }
         };
+        const bool active = true;
         zero_acc<C>(acc);
         gemm_wstream<C, real>(acc, ws, seq, tp.S + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
         if (TERMINAL) {
@@ -910,8 +910,9 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
         const int tile_d = tm.wo % P.ntile_d, kpart = tm.wo / P.ntile_d;
         for (int q = lane; q < P.nseq; q += 32) {
             const bool dwide = q >= P.nseq - 2;
-            const int first = dwide ? kpart : 0, stride = dwide ? P.ksplit : 1;
-            const int cnt = (dwide && kpart >= P.ksplit) ? 0 : (P.seq_K[q] - first + stride - 1) / stride;
+            const int ks_t = (C::NWO - tile_d + P.ntile_d - 1) / P.ntile_d;   // every warp takes a K-slice of its tile
+            const int first = dwide ? kpart : 0, stride = dwide ? ks_t : 1;
+            const int cnt = (P.seq_K[q] - first + stride - 1) / stride;
             M.wtab[warp][q][0] = P.seq_off[q] + first * P.seq_N[q] + (dwide ? tile_d : tm.wo) * C::WB;
             M.wtab[warp][q][1] = stride * P.seq_N[q];
             M.wtab[warp][q][2] = cnt > 0 ? cnt : 0;
@@ -1048,16 +1049,31 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                     }
                     tile_sync<C>();
                 }
-                for (int idx = tid; idx < (d + 4) * TS; idx += NT) {
-                    int row = idx / TS, s = idx % TS;
-                    real kk;
-                    if (row >= d) kk = hstep * sm[tp.SC + (row - d) * TSP + s];
-                    else if (pr.kind == 2) kk = sm[tp.G + row * TSP + s];
-                    else kk = hstep * (-sm[tp.G + row * TSP + s]);
-                    real z0v = zb[Z0 + row * TSP + s];
-                    real zprev = (st == 0) ? z0v : zb[ZA + row * TSP + s];
-                    zb[ZA + row * TSP + s] = zprev + wgt * kk;
-                    if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v + cnext * kk;
+                // RK combination (OCflow.py:172-182).  Four independent (row, sample) items per trip with all loads
+                // first: the augmented state may live in the global scratch, and its latency is paid once per batch.
+                for (int base = tid; base < (d + 4) * TS; base += 4 * NT) {
+                    real kk[4], z0v[4], zpv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * NT;
+                        if (idx < (d + 4) * TS) {
+                            const int row = idx / TS, s = idx % TS;
+                            if (row >= d) kk[u] = hstep * sm[tp.SC + (row - d) * TSP + s];
+                            else if (pr.kind == 2) kk[u] = sm[tp.G + row * TSP + s];
+                            else kk[u] = hstep * (-sm[tp.G + row * TSP + s]);
+                            z0v[u] = zb[Z0 + row * TSP + s];
+                            zpv[u] = (st == 0) ? z0v[u] : zb[ZA + row * TSP + s];
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int idx = base + u * NT;
+                        if (idx < (d + 4) * TS) {
+                            const int row = idx / TS, s = idx % TS;
+                            zb[ZA + row * TSP + s] = zpv[u] + wgt * kk[u];
+                            if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v[u] + cnext * kk[u];
+                        }
+                    }
                 }
                 if (!lastst)
                     for (int s = tid; s < TS; s += NT) sm[tp.S + d * TSP + s] = tnext;
