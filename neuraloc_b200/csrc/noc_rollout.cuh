@@ -403,121 +403,102 @@ __device__ __noinline__ WStream phi_chain(const ThreadMap<C> tm, WStream ws) {
     const Panels& tp = M.tp;
     real* sm = smem_base<real>();
     const int npm = C::WSTREAM ? 1 : P.Npm / PB;
+    const int nTh = P.nTh;
     real acc[RO][RS];
-    int seq = 0;
-
-    // GEMM-1: opening layer (Phi.py:114-115); keeps act(o) in U and tanh(o) in T[0]
-    for (int pass = 0; pass < npm; ++pass) {
-        zero_acc<C>(acc);
-        gemm_m<C>(acc, P, tp, ws, tm, seq, pass, tp.S);
-#pragma unroll
-        for (int ro = 0; ro < RO; ++ro) {
-            int o = pass * PB + tm.orow + ro * WO;
-            if (o < P.m) {
-                real bb = wscalar<C>(P, tp, P.off_b[0] + o);
-                real uu[RS], tt[RS];
-#pragma unroll
-                for (int j = 0; j < RS; ++j) act_tanh(acc[ro][j] + bb, uu[j], tt[j]);
-                st_panel<RS>(sm + tp.U + o * TSP + tm.scol, uu);
-                st_panel<RS>(sm + tp.T[0] + o * TSP + tm.scol, tt);
-            }
-        }
-    }
-    ++seq;
-    tile_sync<C>();
-
-    int cur = tp.U, nxt = tp.U2;
     real pn[RS];
 #pragma unroll
     for (int j = 0; j < RS; ++j) pn[j] = real(0);
+    int cur = tp.U, nxt = tp.U2;
 
-    // forward ResNet layers (Phi.py:118-120): u_i = u_{i-1} + h act(K_i u_{i-1} + b_i)
-    for (int i = 1; i < P.nTh; ++i, ++seq) {
-        const bool last = (i == P.nTh - 1);
+    // The m-wide contractions of one evaluation, in stream order (one code path, so the unrolled FFMA blocks exist
+    // once in the instruction cache):
+    //   q = 0            opening layer (Phi.py:114-115):  u0 = act(K0 s + b0) -> U, tanh -> T[0]
+    //   q = 1..nTh-1     forward layer i = q (Phi.py:118-120): u_i = u_{i-1} + h act(K_i u_{i-1} + b_i); the last one
+    //                    leaves y = tanh(a_i) * w instead (u_{nTh-1} is only needed by Phi.forward, TERMINAL)
+    //   q = nTh..2nTh-2  reverse layer i = 2nTh-1-q (Phi.py:124-131): z_i = z_{i+1} + h K_i'(tanh(a_i) * z_{i+1}),
+    //                    z_nTh = w; the epilogue forms the next y with the tanh of the layer below
+    for (int q = 0; q <= 2 * nTh - 2; ++q) {
+        const int kind = (q == 0) ? 0 : (q < nTh ? 1 : 2);
+        const int layer = (kind == 1) ? q : 2 * nTh - 1 - q;
+        const bool last = (kind == 1) && (layer == nTh - 1);
+        const int in_off = (q == 0) ? tp.S : cur;
+        const int out_off = (q == 0) ? tp.U : nxt;
         for (int pass = 0; pass < npm; ++pass) {
             zero_acc<C>(acc);
-            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, cur);
-            if (nxt == cur) tile_sync<C>();      // in place (single pass): every reader of `cur` is done
+            gemm_m<C>(acc, P, tp, ws, tm, q, pass, in_off);
+            if (q > 0 && nxt == cur) tile_sync<C>();     // in place (single pass): every reader of `cur` is done
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
-                int o = pass * PB + tm.orow + ro * WO;
+                const int o = pass * PB + tm.orow + ro * WO;
                 if (o < P.m) {
-                    real bb = wscalar<C>(P, tp, P.off_b[i] + o);
                     real out[RS];
-                    if (!last) {
-                        real uo[RS], tt[RS];
-                        ld_panel<RS>(sm + cur + o * TSP + tm.scol, uo);
+                    real* po = sm + o * TSP + tm.scol;       // my RS samples of row o, relative to a panel offset
+                    if (kind == 0) {
+                        const real bb = wscalar<C>(P, tp, P.off_b[0] + o);
+                        real tt[RS];
 #pragma unroll
-                        for (int j = 0; j < RS; ++j) {
-                            real av;
-                            act_tanh(acc[ro][j] + bb, av, tt[j]);
-                            out[j] = uo[j] + P.h * av;
-                        }
-                        st_panel<RS>(sm + tp.T[i] + o * TSP + tm.scol, tt);
-                    } else {
-                        real wv = wscalar<C>(P, tp, P.off_w + o);
-                        if (TERMINAL) {          // Phi.forward needs u_{nTh-1} (Phi.py:96): accumulate w . u_last
-                            real uo[RS];
-                            ld_panel<RS>(sm + cur + o * TSP + tm.scol, uo);
+                        for (int j = 0; j < RS; ++j) act_tanh(acc[ro][j] + bb, out[j], tt[j]);
+                        st_panel<RS>(po + tp.T[0], tt);
+                    } else if (kind == 1) {
+                        const real bb = wscalar<C>(P, tp, P.off_b[layer] + o);
+                        if (!last) {
+                            real uo[RS], tt[RS];
+                            ld_panel<RS>(po + cur, uo);
 #pragma unroll
                             for (int j = 0; j < RS; ++j) {
-                                real av, tv;
-                                act_tanh(acc[ro][j] + bb, av, tv);
-                                pn[j] = r_fma(wv, uo[j] + P.h * av, pn[j]);
-                                out[j] = tv * wv;
+                                real av;
+                                act_tanh(acc[ro][j] + bb, av, tt[j]);
+                                out[j] = uo[j] + P.h * av;
                             }
+                            st_panel<RS>(po + tp.T[layer], tt);
                         } else {
+                            const real wv = wscalar<C>(P, tp, P.off_w + o);
+                            if (TERMINAL) {          // Phi.forward needs u_{nTh-1} (Phi.py:96): accumulate w . u_last
+                                real uo[RS];
+                                ld_panel<RS>(po + cur, uo);
 #pragma unroll
-                            for (int j = 0; j < RS; ++j) out[j] = tanh_only(acc[ro][j] + bb) * wv;
+                                for (int j = 0; j < RS; ++j) {
+                                    real av, tv;
+                                    act_tanh(acc[ro][j] + bb, av, tv);
+                                    pn[j] = r_fma(wv, uo[j] + P.h * av, pn[j]);
+                                    out[j] = tv * wv;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < RS; ++j) out[j] = tanh_only(acc[ro][j] + bb) * wv;
+                            }
                         }
-                    }
-                    st_panel<RS>(sm + nxt + o * TSP + tm.scol, out);
-                }
-            }
-        }
-        tile_sync<C>();
-        int t = cur; cur = nxt; nxt = t;
-    }
-    if (TERMINAL) {                              // w . u_last: reduce over the WO lanes that share my samples
-#pragma unroll
-        for (int j = 0; j < RS; ++j)
-#pragma unroll
-            for (int off = 1; off < WO; off <<= 1) pn[j] += __shfl_xor_sync(0xffffffffu, pn[j], off);
-        if (tm.lo == 0) st_panel<RS>(sm + tp.PN + tm.wo * TSP + tm.scol, pn);
-    }
-
-    // reverse sweep (Phi.py:124-131): z_i = z_{i+1} + h K_i' (tanh(a_i) * z_{i+1}), z_{nTh} = w;
-    // `cur` holds y = tanh(a_i) * z_{i+1}; the epilogue forms the next y with tanh of the layer below.
-    for (int i = P.nTh - 1; i >= 1; --i, ++seq) {
-        for (int pass = 0; pass < npm; ++pass) {
-            zero_acc<C>(acc);
-            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, cur);
-            if (nxt == cur) tile_sync<C>();
-#pragma unroll
-            for (int ro = 0; ro < RO; ++ro) {
-                int o = pass * PB + tm.orow + ro * WO;
-                if (o < P.m) {
-                    real zi[RS], tt[RS], out[RS];
-                    if (i == P.nTh - 1) {
-                        real wv = wscalar<C>(P, tp, P.off_w + o);
-#pragma unroll
-                        for (int j = 0; j < RS; ++j) zi[j] = wv + P.h * acc[ro][j];
                     } else {
-                        ld_panel<RS>(sm + tp.Zb + o * TSP + tm.scol, zi);
+                        real zi[RS], tt[RS];
+                        if (layer == nTh - 1) {
+                            const real wv = wscalar<C>(P, tp, P.off_w + o);
 #pragma unroll
-                        for (int j = 0; j < RS; ++j) zi[j] = zi[j] + P.h * acc[ro][j];
+                            for (int j = 0; j < RS; ++j) zi[j] = wv + P.h * acc[ro][j];
+                        } else {
+                            ld_panel<RS>(po + tp.Zb, zi);
+#pragma unroll
+                            for (int j = 0; j < RS; ++j) zi[j] = zi[j] + P.h * acc[ro][j];
+                        }
+                        if (layer > 1) st_panel<RS>(po + tp.Zb, zi);
+                        ld_panel<RS>(po + tp.T[layer - 1], tt);
+#pragma unroll
+                        for (int j = 0; j < RS; ++j) out[j] = tt[j] * zi[j];
                     }
-                    if (i > 1) st_panel<RS>(sm + tp.Zb + o * TSP + tm.scol, zi);
-                    ld_panel<RS>(sm + tp.T[i - 1] + o * TSP + tm.scol, tt);
-#pragma unroll
-                    for (int j = 0; j < RS; ++j) out[j] = tt[j] * zi[j];
-                    st_panel<RS>(sm + nxt + o * TSP + tm.scol, out);
+                    st_panel<RS>(po + out_off, out);
                 }
             }
         }
         tile_sync<C>();
-        int t = cur; cur = nxt; nxt = t;
+        if (q > 0) { const int t = cur; cur = nxt; nxt = t; }
+        if (TERMINAL && last) {                      // w . u_last: reduce over the WO lanes that share my samples
+#pragma unroll
+            for (int j = 0; j < RS; ++j)
+#pragma unroll
+                for (int off = 1; off < WO; off <<= 1) pn[j] += __shfl_xor_sync(0xffffffffu, pn[j], off);
+            if (tm.lo == 0) st_panel<RS>(sm + tp.PN + tm.wo * TSP + tm.scol, pn);
+        }
     }
+    const int seq = 2 * nTh - 1;                     // the two D-wide matrices: sym, then W4
 
     // GEMM-4 (Phi.py:133-136): grad = K0' v + A'A s + c_w'.  The A'A s product is accumulated first so that
     // the terminal pass can keep it (Phi.forward's quadratic term, Phi.py:96) without a second register tile.
@@ -525,15 +506,16 @@ __device__ __noinline__ WStream phi_chain(const ThreadMap<C> tm, WStream ws) {
         const int npd = P.Npd / PB;
         for (int pass = 0; pass < npd; ++pass) {
             zero_acc<C>(acc);
-            gemm_m<C>(acc, P, tp, ws, tm, seq, pass, tp.S);
-            if (TERMINAL) {
+            for (int dq = 0; dq < 2; ++dq) {
+                gemm_m<C>(acc, P, tp, ws, tm, seq + dq, pass, dq == 0 ? tp.S : cur);
+                if (TERMINAL && dq == 0) {
 #pragma unroll
-                for (int ro = 0; ro < RO; ++ro) {
-                    int o = pass * PB + tm.orow + ro * WO;
-                    if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                    for (int ro = 0; ro < RO; ++ro) {
+                        int o = pass * PB + tm.orow + ro * WO;
+                        if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                    }
                 }
             }
-            gemm_m<C>(acc, P, tp, ws, tm, seq + 1, pass, cur);
             if (tp.G == cur) tile_sync<C>();     // G aliases the hidden panel (single pass): readers are done
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
@@ -550,50 +532,47 @@ __device__ __noinline__ WStream phi_chain(const ThreadMap<C> tm, WStream ws) {
         tile_sync<C>();
     } else {
         // streamed configurations: D is much narrower than the CTA's output span, so the warps are re-tiled as
-        // ntile_d output tiles x ksplit slices of every slab's rows; slices >= 1 hand their partial sums to slice 0
-        // through panel GP.
+        // ntile_d output tiles, every warp taking a K-slice of its tile's rows; slices >= 1 hand their partial sums
+        // to slice 0 through panel GP, one slice per round.
         const int tile_d = tm.wo % P.ntile_d, kpart = tm.wo / P.ntile_d;
         const int orow = tile_d * C::WB + tm.lo;
         const int ks_t = (C::NWO - tile_d + P.ntile_d - 1) / P.ntile_d;      // K-slices of my output tile
-        auto exchange = [&]() {                  // sum the K-slices into slice 0, one slice per round (all warps call this)
-            for (int round = 1; round < P.ksplit; ++round) {
-                if (kpart == round) {
+        zero_acc<C>(acc);
+        for (int dq = 0; dq < 2; ++dq) {
+            gemm_wstream<C, real>(acc, ws, seq + dq, (dq == 0 ? tp.S : cur) + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
+            if (dq == 1 || TERMINAL) {
+                for (int round = 1; round < P.ksplit; ++round) {     // all warps walk the rounds
+                    if (kpart == round) {
 #pragma unroll
-                    for (int ro = 0; ro < RO; ++ro) st_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, acc[ro]);
+                        for (int ro = 0; ro < RO; ++ro) st_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, acc[ro]);
+                    }
+                    __syncthreads();
+                    if (kpart == 0 && round < ks_t) {
+#pragma unroll
+                        for (int ro = 0; ro < RO; ++ro) {
+                            real t[RS];
+                            ld_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, t);
+#pragma unroll
+                            for (int j = 0; j < RS; ++j) acc[ro][j] += t[j];
+                        }
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                if (kpart == 0 && round < ks_t) {
+                if (dq == 0) {                   // TERMINAL: keep A'A s; the other slices restart from zero
+                    if (kpart == 0) {
 #pragma unroll
-                    for (int ro = 0; ro < RO; ++ro) {
-                        real t[RS];
-                        ld_panel<RS>(sm + tp.GP + (orow + ro * WO) * TSP + tm.scol, t);
-#pragma unroll
-                        for (int j = 0; j < RS; ++j) acc[ro][j] += t[j];
+                        for (int ro = 0; ro < RO; ++ro) {
+                            int o = orow + ro * WO;
+                            if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
+                        }
+                    } else {
+                        zero_acc<C>(acc);
                     }
                 }
-                if (round + 1 < P.ksplit) __syncthreads();
             }
-        };
-        const bool active = true;
-        zero_acc<C>(acc);
-        gemm_wstream<C, real>(acc, ws, seq, tp.S + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
-        if (TERMINAL) {
-            exchange();
-            if (active && kpart == 0) {
-#pragma unroll
-                for (int ro = 0; ro < RO; ++ro) {
-                    int o = orow + ro * WO;
-                    if (o < P.D) st_panel<RS>(sm + tp.Qs + o * TSP + tm.scol, acc[ro]);
-                }
-            } else {
-                zero_acc<C>(acc);
-            }
-            __syncthreads();                     // GP is reused by the second exchange
         }
-        gemm_wstream<C, real>(acc, ws, seq + 1, cur + tm.scol, tm.lo, tm.tid >> 5, tm.tid & 31);
-        exchange();
-        __syncthreads();                         // every reader of `cur` (which G may alias) and of GP is done
-        if (active && kpart == 0) {
+        __syncthreads();                         // every reader of `cur` (which G may alias) is done
+        if (kpart == 0) {
 #pragma unroll
             for (int ro = 0; ro < RO; ++ro) {
                 int o = orow + ro * WO;
