@@ -256,28 +256,38 @@ __device__ __forceinline__ void fma_tile(real (&acc)[C::RO][C::RS], const real (
 }
 
 // WSMEM configurations: acc[RO][RS] += sum_k W[k][pcol..pcol+RO) * in[k][scol..scol+RS), weights from the staged
-// copy of the blob.  Software-pipelined in registers (weights 4 k-steps ahead, activations 1); loads past K are
-// clamped to row K-1 (valid memory, unused), the FFMA block of a step past K is skipped.
+// copy of the blob.  Groups of 4 k-steps run straight-line with register double-buffering (the next step's two
+// vectors are loaded while the current step's FFMA block issues); the K % 4 tail is a plain loop.
 template <class C, typename real>
 __device__ __forceinline__ void gemm_acc(real (&acc)[C::RO][C::RS], int woff, int ldw, int in_off, int K) {
-    constexpr int PF = 4;
     const real* in = smem_base<real>() + in_off;
     const real* W = smem_base<real>() + woff;
-    real wq[PF][C::RO], a[2][C::RS];
-    const int kl = K - 1;
+    real wq[2][C::RO], a[2][C::RS];
+    int k = 0;
+    if (K >= 4) {
+        ld_wrow<C>(W, wq[0]);
+        ld_panel<C::RS>(in, a[0]);
+        for (; k + 4 <= K; k += 4) {
+            const real* Wk = W + k * ldw;
+            const real* ik = in + k * C::TSP;
+            const bool more = (k + 8 <= K);          // another full group follows: prefetch its first step
 #pragma unroll
-    for (int u = 0; u < PF; ++u) ld_wrow<C>(W + ((u < kl) ? u : kl) * ldw, wq[u]);
-    ld_panel<C::RS>(in, a[0]);
-    for (int k = 0; k < K; k += PF) {
-#pragma unroll
-        for (int u = 0; u < PF; ++u) {
-            const int kk = k + u;
-            const int kn = (kk + 1 < kl) ? kk + 1 : kl;
-            ld_panel<C::RS>(in + kn * C::TSP, a[(u + 1) & 1]);
-            if (kk < K) fma_tile<C>(acc, wq[u], a[u & 1]);
-            const int kw = (kk + PF < kl) ? kk + PF : kl;
-            ld_wrow<C>(W + kw * ldw, wq[u]);
+            for (int u = 0; u < 4; ++u) {
+                if (u < 3) {
+                    ld_wrow<C>(Wk + (u + 1) * ldw, wq[(u + 1) & 1]);
+                    ld_panel<C::RS>(ik + (u + 1) * C::TSP, a[(u + 1) & 1]);
+                } else if (more) {
+                    ld_wrow<C>(Wk + 4 * ldw, wq[0]);
+                    ld_panel<C::RS>(ik + 4 * C::TSP, a[0]);
+                }
+                fma_tile<C>(acc, wq[u & 1], a[u & 1]);
+            }
         }
+    }
+    for (; k < K; ++k) {
+        ld_wrow<C>(W + k * ldw, wq[0]);
+        ld_panel<C::RS>(in + k * C::TSP, a[0]);
+        fma_tile<C>(acc, wq[0], a[0]);
     }
 }
 
