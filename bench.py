@@ -153,6 +153,60 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def latency_mode(args, W, dtype, threads):
+    """Batch-1 rollout latency: ONE OCflow(xInit) call, wall clock, CPU tensors in and out — the protocol of
+    timeDeployment/timeOC.py:76-81 (nt = 50; 80 for swarm50 as in README.md:85) — beside the CPU oracle port timed on
+    one thread (the published numbers were taken under `taskset -c 0`, README.md:152-155)."""
+    import neuraloc_b200 as nb
+    from oracle import ocflow_oracle as orc
+    from helpers import load_ckpt
+    nb._cabi.lib()
+    torch.cuda.set_device(0)
+    nt = W["nt"]
+    net, prob, xinit, meta = build_case(args.workload, torch.device("cpu"), dtype)      # CPU tensors, like timeOC.py
+    alph = meta["alph"]
+    with torch.no_grad():
+        for _ in range(5):
+            nb.OCflow(xinit, net, prob, [0.0, 1.0], nt, "rk4", alph)
+        wall = []
+        for _ in range(200):
+            t0 = time.perf_counter()
+            Jc, cs = nb.OCflow(xinit, net, prob, [0.0, 1.0], nt, "rk4", alph)        # H2D + rollout + D2H + sync inside
+            wall.append(time.perf_counter() - t0)
+        xd = xinit.cuda()
+        netd = net.cuda()
+        ev = []
+        for _ in range(100):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); nb.ocflow_sums(xd, netd, prob, [0.0, 1.0], nt, "rk4", alph); e1.record()
+            ev.append((e0, e1))
+        torch.cuda.synchronize()
+        dev_ms = statistics.median(a.elapsed_time(b) for a, b in ev)
+        # CPU oracle port, one thread
+        torch.set_num_threads(1)
+        if W["ckpt"] is None:
+            sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        else:
+            sd, _ = load_ckpt(W["ckpt"])
+        P = orc.params_from_state_dict(sd, dtype)
+        D, xi = orc.make_problem(meta["data"], alph, dtype)
+        orc.ocflow(xi, P, D, [0.0, 1.0], nt, "rk4", alph)
+        cpu = []
+        for _ in range(5):
+            t0 = time.perf_counter()
+            Jr, _ = orc.ocflow(xi, P, D, [0.0, 1.0], nt, "rk4", alph)
+            cpu.append(time.perf_counter() - t0)
+    line = {"metric": "batch1_rollout_latency", "value": statistics.median(wall) * 1e3, "unit": "ms", "n_gpus": 1,
+            "higher_is_better": False, "dtype": W["dtype"], "data": "xInit of the problem",
+            "config": {"workload": "%s, one OCflow(xInit) call, nt=%d, CPU tensors in/out (timeOC.py:76-81)" % (args.workload, nt)},
+            "host_wall_ms": {"median": statistics.median(wall) * 1e3, "p10": sorted(wall)[20] * 1e3, "p90": sorted(wall)[180] * 1e3},
+            "device_ms_median": dev_ms, "ms_per_rk4_step": statistics.median(wall) * 1e3 / nt,
+            "cpu_baseline": {"value": statistics.median(cpu) * 1e3, "unit": "ms", "cores": 1, "kind": "port",
+                             "sample": "median of 5 warm calls of the torch-CPU oracle port, 1 thread"},
+            "Jc": float(Jc), "Jc_cpu": float(Jr)}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -160,8 +214,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="swap12", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=0, help="samples per GPU (default: the workload's)")
+    ap.add_argument("--samples", dest="n", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--latency", action="store_true", help="batch-1 rollout latency (timeDeployment/timeOC.py protocol) instead of throughput")
     args = ap.parse_args()
     W = WORKLOADS[args.workload]
     n = args.n or W["n"]
@@ -192,6 +247,9 @@ def main():
                 "gpu_launches": 0}
         print(json.dumps(line))
         return
+
+    if args.latency:
+        return latency_mode(args, W, dtype, threads)
 
     # ------------------------------------------------------------------ our arm
     import neuraloc_b200 as nb

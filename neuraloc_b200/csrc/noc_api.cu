@@ -244,6 +244,13 @@ int device_facts() {
     NOC_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
     NOC_CUDA(cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev));
     NOC_CUDA(cudaDeviceGetAttribute(&g_cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    // scratch comes from the stream-ordered pool on every call: keep freed blocks cached instead of returning them
+    // to the driver at each synchronisation (the default threshold of 0 re-allocates 100 MB inputs every call)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long keep = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     g_smem_optin = v;
     return NOC_OK;
 }

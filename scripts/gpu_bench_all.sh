@@ -4,9 +4,9 @@ mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q --maxfail=40 --tb=short -p no:cacheprovider > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke_$TAG.log 2>&1; echo "smoke rc=$?" >> gpurun_out/smoke_$TAG.log
 for W in swap12 softcorridor swap2; do timeout 300 python bench.py --steps 3 --warmup 3 --workload $W --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_${W}_$TAG.json; done
-timeout 300 python bench.py --steps 2 --warmup 3 --workload singlequad --n 524288 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_singlequad_$TAG.json
-timeout 300 python bench.py --steps 2 --warmup 3 --workload swarm50 --n 65536 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_swarm50_$TAG.json
-timeout 300 python bench.py --steps 2 --warmup 3 --workload config5 --n 16384 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_config5_$TAG.json
+timeout 300 python bench.py --steps 2 --warmup 3 --workload singlequad --samples 524288 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_singlequad_$TAG.json
+timeout 300 python bench.py --steps 2 --warmup 3 --workload swarm50 --samples 65536 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_swarm50_$TAG.json
+timeout 300 python bench.py --steps 2 --warmup 3 --workload config5 --samples 16384 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_config5_$TAG.json
 tail -3 gpurun_out/pytest_gpu_$TAG.log; tail -2 gpurun_out/smoke_$TAG.log
 python - <<PY
 import json,glob
