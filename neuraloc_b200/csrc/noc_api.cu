@@ -397,10 +397,25 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     else if (mode == NOC_MODE_MEAN || mode == NOC_MODE_NOMEAN) { if (!out_costs) return fail(NOC_ERR_ARG, "out_costs is NULL"); }
     else return fail(NOC_ERR_ARG, "unknown mode %d", mode);
 
+    // path: small batches run one CTA per sample (noc_vec.cu), everything else the tile kernel.
+    // NOC_VEC_MAX sets the batch-size threshold, NOC_FORCE_PATH=tile|vec pins a path (tests).
+    rc = device_facts();
+    if (rc) return rc;
+    long long vec_max = 256;
+    if (const char* e = getenv("NOC_VEC_MAX")) vec_max = atoll(e);
+    bool use_vec = n <= vec_max;
+    if (const char* e = getenv("NOC_FORCE_PATH")) {
+        if (!strcmp(e, "vec")) use_vec = true;
+        else if (!strcmp(e, "tile")) use_vec = false;
+    }
+    if (std::max(ph->m, ph->d + 4) > 1024) use_vec = false;
+
     int cfg_id = -1;
     size_t smem = 0;
-    rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
-    if (rc) return rc;
+    if (!use_vec) {
+        rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
+        if (rc) return rc;
+    }
 
     std::vector<double> tab((size_t)nt * 5);
     if (stage_times) memcpy(tab.data(), stage_times, sizeof(double) * tab.size());
@@ -414,7 +429,12 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     A.t_end = (real)t1;
     A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
     A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
-    rc = dispatch<real>(cfg_id, A, &R, KMODE_ROLLOUT, smem, st, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr);
+    if (use_vec)
+        rc = vec_rollout<real>(ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph,
+                               t1, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c,
+                               g_smem_optin, st);
+    else
+        rc = dispatch<real>(cfg_id, A, &R, KMODE_ROLLOUT, smem, st, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr);
     cudaError_t e = cudaFreeAsync(dtab, st);
     if (rc) return rc;
     if (e != cudaSuccess) return fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));

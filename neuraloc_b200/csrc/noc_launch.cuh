@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstring>
 
 #include "../../include/noc_b200.h"
 #include "noc_rollout.cuh"
@@ -33,6 +34,12 @@ using CfgF_L = Cfg<float, 8, 8, 8, 8, 1, false>;    // id 3, m <= 512: 32 sample
 using CfgD_S8 = Cfg<double, 8, 4, 4, 1, 4, true>;   // id 4
 using CfgD_M = Cfg<double, 8, 4, 8, 2, 4, false>;   // id 5
 using CfgD_L = Cfg<double, 8, 4, 8, 8, 1, false>;   // id 6
+
+// small-batch path (noc_vec.cu): one CTA per sample, one thread per hidden unit
+template <typename real>
+int vec_rollout(int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw, const ProbPack& pr, const real* x, long long n,
+                const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
+                real* out_nomean, real* zFull, real* ctrlFull, int smem_limit, cudaStream_t st);
 
 // one translation unit per configuration (noc_inst.cu with -DNOC_CFG_ID=k) defines these
 #define NOC_DECL_LAUNCH(ID, REAL) \

@@ -16,6 +16,14 @@ pytestmark = pytest.mark.gpu
 TOL = {"f32": dict(state=1e-5, cost=1e-4, floor=2e-4, ctrl=2e-4), "f64": dict(state=1e-11, cost=1e-9, floor=1e-10, ctrl=1e-9)}
 
 
+@pytest.fixture(autouse=True, params=["tile", "vec"])
+def path(request, monkeypatch):
+    """Every rollout test runs through both kernels: the sample-tile kernel (large batches) and the one-CTA-per-sample
+    kernel (small batches / deployment latency).  NOC_FORCE_PATH pins the choice the host would make by batch size."""
+    monkeypatch.setenv("NOC_FORCE_PATH", request.param)
+    return request.param
+
+
 @pytest.fixture(scope="module")
 def nb():
     import neuraloc_b200
@@ -188,10 +196,11 @@ def test_rollout_vs_oracle_ragged_batches(nb, name):
 
 
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6])
-def test_every_tile_configuration_agrees(nb, cfg, monkeypatch):
+def test_every_tile_configuration_agrees(nb, cfg, monkeypatch, path):
     """Forces each tile configuration (multi-pass GEMMs, ping-pong panels, TPS > 1 problem phase) on swap12 and a
     deep net; results must not depend on the tiling."""
-    from oracle import ocflow_oracle as orc
+    if path != "tile":
+        pytest.skip("tile configurations only exist on the tile path")
     dtype = torch.float32 if cfg < 4 else torch.float64
     tag = "f32" if cfg < 4 else "f64"
     monkeypatch.setenv("NOC_FORCE_CFG", str(cfg))
@@ -279,6 +288,22 @@ def test_config5_random_init_swarm50_shape_fp64(nb):
     assert rel_err(cf[:, :, -1], z["ctrl_last_f64"], floor=1.0) <= 1e-9
     sc = np.maximum(np.abs(z["nomean_f64"]).max(axis=0, keepdims=True), 1.0)
     assert (np.abs(nomean - z["nomean_f64"]) / sc).max() <= 1e-9
+
+
+def test_default_path_selection_by_batch_size(nb, monkeypatch):
+    """Without NOC_FORCE_PATH the host picks the small-batch kernel up to NOC_VEC_MAX samples and the tile kernel above;
+    the two agree to rounding."""
+    monkeypatch.delenv("NOC_FORCE_PATH", raising=False)
+    net, prob, xinit, meta = product_setup("swap12", torch.float32)
+    g = torch.Generator().manual_seed(9)
+    x = (xinit.cpu() + torch.randn(300, 24, generator=g)).cuda()
+    with torch.no_grad():
+        monkeypatch.setenv("NOC_VEC_MAX", "1000")
+        a = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], 20, "rk4", meta["alph"]))
+        monkeypatch.setenv("NOC_VEC_MAX", "10")
+        b = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], 20, "rk4", meta["alph"]))
+    check_costs(a, b, 2e-5, 1e-5, "vec vs tile path")
+    assert not np.array_equal(a, b)          # different kernels, different summation orders
 
 
 def test_input_is_not_mutated_and_errors_are_loud(nb):
