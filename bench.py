@@ -204,7 +204,7 @@ def latency_mode(args, W, dtype, threads):
             "cpu_baseline": {"value": statistics.median(cpu) * 1e3, "unit": "ms", "cores": 1, "kind": "port",
                              "sample": "median of 5 warm calls of the torch-CPU oracle port, 1 thread"},
             "Jc": float(Jc), "Jc_cpu": float(Jr)}
-    print(json.dumps(line))
+    return line
 
 
 def main():
@@ -249,7 +249,8 @@ def main():
         return
 
     if args.latency:
-        return latency_mode(args, W, dtype, threads)
+        print(json.dumps(latency_mode(args, W, dtype, threads)))
+        return
 
     # ------------------------------------------------------------------ our arm
     import neuraloc_b200 as nb
@@ -353,6 +354,10 @@ def main():
                                         "MEASURED_PEAKS.json has no FP32/FP64 FMA figure"},
         }
         if world == 1 and not args.no_cpu_baseline:
+            lat = latency_mode(args, W, dtype, threads)     # the other half of BASELINE.json's metric
+            line["batch1_latency"] = {"value": lat["value"], "unit": "ms", "device_ms": lat["device_ms_median"],
+                                      "ms_per_rk4_step": lat["ms_per_rk4_step"], "protocol": lat["config"]["workload"],
+                                      "cpu_port_1thread_ms": lat["cpu_baseline"]["value"]}
             r, dt = cpu_rate(args.workload, W["n_cpu"], nt, dtype, threads)
             line["cpu_baseline"] = {"value": r, "unit": "sample-steps/s", "cores": threads, "kind": "port",
                                     "sample": "%d of the %d samples, nt=%d, one call, %.1f s; torch CPU %s oracle port (the Python reference cannot travel)"

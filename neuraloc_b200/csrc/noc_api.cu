@@ -121,19 +121,21 @@ static __global__ void __launch_bounds__(32 * WARPS) fma_tile_peak_kernel(float*
 
 struct CfgInfo {
     int id, PB, WB, NWO, TS, TSP, NT, TPS, GRP;
-    bool wsmem;
+    bool wsmem, zglobal;
     size_t elt;
     const char* name;
 };
 template <class C>
 static CfgInfo info_of(int id, const char* name) {
-    return CfgInfo{id, C::PB, C::WB, C::NWO, C::TS, C::TSP, C::NT, C::TPS, C::GRP, C::WSMEM, sizeof(typename C::real), name};
+    return CfgInfo{id, C::PB, C::WB, C::NWO, C::TS, C::TSP, C::NT, C::TPS, C::GRP, C::WSMEM, C::ZGLOBAL, sizeof(typename C::real), name};
 }
 static const CfgInfo kCfgs[] = {
     info_of<CfgF_S4>(0, "f32/small4"), info_of<CfgF_S8>(1, "f32/small8"), info_of<CfgF_M>(2, "f32/mid"),
     info_of<CfgF_L>(3, "f32/large"),   info_of<CfgD_S8>(4, "f64/small8"), info_of<CfgD_M>(5, "f64/mid"),
-    info_of<CfgD_L>(6, "f64/large"),
+    info_of<CfgD_L>(6, "f64/large"),   info_of<CfgF_S8Z>(7, "f32/small8z"), info_of<CfgF_S4Z>(8, "f32/small4z"),
 };
+static const int kNumCfgs = 9;
+static inline bool cfg_is_f64(int id) { return id >= 4 && id <= 6; }
 
 // blob layout + padded widths for configuration `ci`.  The matrices are laid out in the order one grad-Phi
 // evaluation consumes them (the streamed configurations prefetch along that order).  Returns false when the
@@ -181,8 +183,8 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
     SmemPlan best{};
     size_t best_bytes = 0;
     long best_score = -1;
-    for (int zg = 0; zg < 2; ++zg) {                 // zg = 1: augmented state in a global scratch (frees shared memory)
-        if (zg == 1 && ci.wsmem) break;
+    for (int zg = ci.zglobal ? 1 : 0; zg < 2; ++zg) { // zg = 1: augmented state in a global scratch (frees shared memory)
+        if (zg == 1 && ci.wsmem && !ci.zglobal) break;
         int row = 0;
         auto take = [&](int n) { int o = row; row += n; return o; };
         sp.U = take(std::max(m, D));
@@ -198,7 +200,7 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
         sp.Z0 = zg ? 0 : take(d + 4);
         sp.ZA = zg ? 0 : take(d + 4);
         sp.SC = take(SC_ROWS);
-        sp.RED = take(3 * ci.TPS);
+        sp.RED = (ci.TPS > 1) ? take(3 * ci.TPS) : 0;
         sp.PN = take(ci.NWO);
         sp.QX = (kind == NOC_PROB_QUADCOPTER) ? take(5 * nAgents) : 0;
         // K-split partial sums: inside T[0] above the rows Qs uses when there is room (T[0] is dead by GEMM-4)
@@ -260,11 +262,11 @@ static std::vector<int> candidates(int dtype, int m) {
     const char* f = getenv("NOC_FORCE_CFG");
     if (f && *f) {
         int id = atoi(f);
-        if (id >= 0 && id < 7 && ((id >= 4) == (dtype == NOC_F64))) return {id};
+        if (id >= 0 && id < kNumCfgs && (cfg_is_f64(id) == (dtype == NOC_F64))) return {id};
     }
     if (dtype == NOC_F32) {
-        if (m <= 16) return {0, 1, 2, 3};
-        if (m <= 64) return {1, 2, 3};
+        if (m <= 16) return {0, 8, 7, 1, 2, 3};     // measured: the 4-warp tile is faster than the 15-warp one for m = 16
+        if (m <= 64) return {7, 1, 2, 3};
         if (m <= 256) return {2, 3};
         return {3};
     }
@@ -284,6 +286,8 @@ int dispatch<float>(int cfg_id, const RolloutArgs<float>& A, const PhiRaw<float>
         case 1: return launch_cfg_1(A, raw, kmode, smem, st, out_sums);
         case 2: return launch_cfg_2(A, raw, kmode, smem, st, out_sums);
         case 3: return launch_cfg_3(A, raw, kmode, smem, st, out_sums);
+        case 7: return launch_cfg_7(A, raw, kmode, smem, st, out_sums);
+        case 8: return launch_cfg_8(A, raw, kmode, smem, st, out_sums);
     }
     return fail(NOC_ERR_ARG, "bad f32 configuration id %d", cfg_id);
 }

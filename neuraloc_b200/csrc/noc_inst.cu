@@ -1,9 +1,9 @@
-// noc_inst.cu — instantiates the rollout kernel for ONE tile configuration (-DNOC_CFG_ID=0..6) so that the
-// seven configurations compile in parallel.
+// noc_inst.cu — instantiates the rollout kernel for ONE tile configuration (-DNOC_CFG_ID=0..8) so that the
+// configurations compile in parallel.
 #include "noc_launch.cuh"
 
 #ifndef NOC_CFG_ID
-#error "compile with -DNOC_CFG_ID=<0..6>"
+#error "compile with -DNOC_CFG_ID=<0..8>"
 #endif
 
 namespace noc {
@@ -26,5 +26,9 @@ NOC_DEF_LAUNCH(4, CfgD_S8, double)
 NOC_DEF_LAUNCH(5, CfgD_M, double)
 #elif NOC_CFG_ID == 6
 NOC_DEF_LAUNCH(6, CfgD_L, double)
+#elif NOC_CFG_ID == 7
+NOC_DEF_LAUNCH(7, CfgF_S8Z, float)
+#elif NOC_CFG_ID == 8
+NOC_DEF_LAUNCH(8, CfgF_S4Z, float)
 #endif
 }  // namespace noc

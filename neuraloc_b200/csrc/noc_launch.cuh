@@ -34,6 +34,8 @@ using CfgF_L = Cfg<float, 8, 8, 8, 8, 1, false>;    // id 3, m <= 512: 32 sample
 using CfgD_S8 = Cfg<double, 8, 4, 4, 1, 4, true>;   // id 4
 using CfgD_M = Cfg<double, 8, 4, 8, 2, 4, false>;   // id 5
 using CfgD_L = Cfg<double, 8, 4, 8, 8, 1, false>;   // id 6
+using CfgF_S8Z = Cfg<float, 8, 4, 4, 1, 15, true, true>;   // id 7, m <= 64: one 15-warp CTA per SM, warp-private tiles, state in global scratch
+using CfgF_S4Z = Cfg<float, 4, 4, 4, 1, 15, true, true>;   // id 8, m <= 16: same
 
 // small-batch path (noc_vec.cu): one CTA per sample, one thread per hidden unit
 template <typename real>
@@ -51,6 +53,8 @@ NOC_DECL_LAUNCH(3, float)
 NOC_DECL_LAUNCH(4, double)
 NOC_DECL_LAUNCH(5, double)
 NOC_DECL_LAUNCH(6, double)
+NOC_DECL_LAUNCH(7, float)
+NOC_DECL_LAUNCH(8, float)
 
 template <class C, typename real>
 int launch_cfg(const RolloutArgs<real>& A0, const PhiRaw<real>* raw, int kmode, size_t smem_bytes,

@@ -25,7 +25,7 @@ namespace noc {
 // ------------------------------------------------------------------------------------------------
 // tile configuration
 // ------------------------------------------------------------------------------------------------
-template <typename real_, int RO_, int RS_, int WO_, int NWO_, int NWS_, bool WSMEM_>
+template <typename real_, int RO_, int RS_, int WO_, int NWO_, int NWS_, bool WSMEM_, bool ZGLOBAL_ = false>
 struct Cfg {
     using real = real_;
     static constexpr int RO = RO_;            // outputs per thread
@@ -44,11 +44,17 @@ struct Cfg {
     static constexpr int PAD = (sizeof(real_) == 4) ? (WO_ >= 8 ? 4 : 8) : (WO_ >= 8 ? 2 : 4);
     static constexpr int TSP = TS + PAD;
     static constexpr bool WSMEM = WSMEM_;     // whole weight blob staged in shared memory (small nets) ...
+    // the augmented state [x, L, HJt, Q, W] (two panels of d+4 rows) lives in a per-CTA global scratch instead of
+    // shared memory: frees a third of the per-sample footprint of small nets, i.e. almost twice the resident warps
+    static constexpr bool ZGLOBAL = ZGLOBAL_;
     static constexpr bool WSTREAM = !WSMEM_;  // ... or streamed through warp-private cp.async rings (m >= 128)
     static constexpr int GRP = (sizeof(real_) == 4) ? 8 : 4;   // rows per cp.async group of a warp's weight stream
     // a warp owns all outputs of its own samples and one thread owns one sample in the problem phase:
     // tiles are warp-private and __syncwarp() replaces __syncthreads()
-    static constexpr bool WARP_PRIVATE = (NWO_ == 1) && (TPS == 1);
+    // ... unless the CTA is one big 15-warp tile: there the warps are kept in lockstep with block barriers, because 15
+    // warps drifting through ~40 KB of straight-line code thrash the instruction cache (measured: 28 % of stall
+    // samples were instruction-fetch stalls when drifting, and lockstep is 20 % faster)
+    static constexpr bool WARP_PRIVATE = (NWO_ == 1) && (TPS == 1) && !ZGLOBAL_;
     static_assert(NT % TS == 0, "threads per sample must be integral");
     static_assert(RS_ * sizeof(real_) % 16 == 0 && RO_ * sizeof(real_) % 16 == 0, "16-byte vector tiles");
 };
@@ -861,12 +867,10 @@ __device__ __forceinline__ void carve(const SmemPlan& sp, Panels& tp) {
 // S[0..d) <- rows of `src` (a [row][TSP] panel in shared memory or in the global scratch), S[d] <- t
 template <class C, typename real>
 __device__ __forceinline__ void stage_input_from(const Panels& tp, const real* src, int d, real t, int tid) {
-    constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
+    constexpr int TS = C::TS, TSP = C::TSP;
     real* sm = smem_base<real>();
-    for (int idx = tid; idx < (d + 1) * TS; idx += NT) {
-        int row = idx / TS, s = idx % TS;
-        sm[tp.S + row * TSP + s] = (row < d) ? src[row * TSP + s] : t;
-    }
+    const int s = tid % TS;
+    for (int row = tid / TS; row <= d; row += C::TPS) sm[tp.S + row * TSP + s] = (row < d) ? src[row * TSP + s] : t;
 }
 
 template <class C, typename real>
@@ -874,7 +878,7 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
     constexpr int TS = C::TS, TSP = C::TSP, NT = C::NT;
     real* sm = smem_base<real>();
     static_assert(sizeof(Meta<real>) <= META_BYTES, "Meta must fit in its reserved shared-memory header");
-    static_assert(C::NT / 32 <= META_WARPS, "wtab holds META_WARPS warps");
+    static_assert(!C::WSTREAM || C::NT / 32 <= META_WARPS, "wtab holds META_WARPS warps");
     Meta<real>& M = meta<real>();
     const ThreadMap<C> tm;
     const int tid = tm.tid;
@@ -915,7 +919,8 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
     }
     __syncthreads();
     // augmented state panels: shared memory, or this CTA's slice of the global scratch (large nets)
-    real* zb = (C::WSTREAM && A.sp.z_global) ? (A.zscratch + (size_t)blockIdx.x * A.zstride) : sm;
+    const bool zglob = C::ZGLOBAL || (C::WSTREAM && A.sp.z_global);
+    real* zb = zglob ? (A.zscratch + (size_t)blockIdx.x * A.zstride) : sm;
 
     double csum = 0.0;                    // threads 0..6: this CTA's running sum of cost q (mean mode)
     long long cnt = 0;
@@ -987,13 +992,13 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
 
         // ---------------------------------------------------------------- rollout (OCflow.py:7-95)
         int Z0 = tp.Z0, ZA = tp.ZA;
-        if (C::WSTREAM && A.sp.z_global) { Z0 = 0; ZA = (d + 4) * TSP; }
+        if (zglob) { Z0 = 0; ZA = (d + 4) * TSP; }
         for (int idx = tid; idx < TS * d; idx += NT) {       // z = [x, 0, 0, 0, 0]  (OCflow.py:33)
             int s = idx / d, c = idx % d;
             long long gs = s0 + (s < nvalid ? s : nvalid - 1);   // padding samples replay the last valid one
             zb[Z0 + c * TSP + s] = A.x[gs * d + c];
         }
-        for (int idx = tid; idx < 4 * TS; idx += NT) zb[Z0 + (d + idx / TS) * TSP + idx % TS] = real(0);
+        for (int row = tid / TS; row < 4; row += C::TPS) zb[Z0 + (d + row) * TSP + tid % TS] = real(0);
         __syncthreads();
 
         const bool inter = (A.mode == 2);
@@ -1031,8 +1036,8 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 problem_phase<C, real>(d, tid);            // SC <- L, |Phi_t - H|, Q, W
 
                 if (pr.kind == 2) {                           // Quadcopter rates read other rows of S: K first, then update
-                    for (int idx = tid; idx < d * TS; idx += NT) {
-                        int row = idx / TS, s = idx % TS;
+                    for (int row = tid / TS; row < d; row += C::TPS) {
+                        const int s = tid % TS;
                         real f = state_rate<C, real>(pr, tp, row, s);
                         sm[tp.G + row * TSP + s] = hstep * f;
                     }
@@ -1040,27 +1045,28 @@ __global__ void __launch_bounds__(C::NT) rollout_kernel(const RolloutArgs<real> 
                 }
                 // RK combination (OCflow.py:172-182).  Four independent (row, sample) items per trip with all loads
                 // first: the augmented state may live in the global scratch, and its latency is paid once per batch.
-                for (int base = tid; base < (d + 4) * TS; base += 4 * NT) {
-                    real kk[4], z0v[4], zpv[4];
+                {
+                    const int s = tid % TS;
+                    for (int row0 = tid / TS; row0 < d + 4; row0 += 4 * C::TPS) {
+                        real kk[4], z0v[4], zpv[4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int idx = base + u * NT;
-                        if (idx < (d + 4) * TS) {
-                            const int row = idx / TS, s = idx % TS;
-                            if (row >= d) kk[u] = hstep * sm[tp.SC + (row - d) * TSP + s];
-                            else if (pr.kind == 2) kk[u] = sm[tp.G + row * TSP + s];
-                            else kk[u] = hstep * (-sm[tp.G + row * TSP + s]);
-                            z0v[u] = zb[Z0 + row * TSP + s];
-                            zpv[u] = (st == 0) ? z0v[u] : zb[ZA + row * TSP + s];
+                        for (int u = 0; u < 4; ++u) {
+                            const int row = row0 + u * C::TPS;
+                            if (row < d + 4) {
+                                if (row >= d) kk[u] = hstep * sm[tp.SC + (row - d) * TSP + s];
+                                else if (pr.kind == 2) kk[u] = sm[tp.G + row * TSP + s];
+                                else kk[u] = hstep * (-sm[tp.G + row * TSP + s]);
+                                z0v[u] = zb[Z0 + row * TSP + s];
+                                zpv[u] = (st == 0) ? z0v[u] : zb[ZA + row * TSP + s];
+                            }
                         }
-                    }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int idx = base + u * NT;
-                        if (idx < (d + 4) * TS) {
-                            const int row = idx / TS, s = idx % TS;
-                            zb[ZA + row * TSP + s] = zpv[u] + wgt * kk[u];
-                            if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v[u] + cnext * kk[u];
+                        for (int u = 0; u < 4; ++u) {
+                            const int row = row0 + u * C::TPS;
+                            if (row < d + 4) {
+                                zb[ZA + row * TSP + s] = zpv[u] + wgt * kk[u];
+                                if (!lastst && row < d) sm[tp.S + row * TSP + s] = z0v[u] + cnext * kk[u];
+                            }
                         }
                     }
                 }

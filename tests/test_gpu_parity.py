@@ -195,20 +195,23 @@ def test_rollout_vs_oracle_ragged_batches(nb, name):
         check_costs(mean[6:], ref_nm[:n, 6:].mean(axis=0), 1e-4, 2e-4, "%s n=%d Q/W" % (name, n))
 
 
-@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6])
+@pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8])
 def test_every_tile_configuration_agrees(nb, cfg, monkeypatch, path):
     """Forces each tile configuration (multi-pass GEMMs, ping-pong panels, TPS > 1 problem phase) on swap12 and a
     deep net; results must not depend on the tiling."""
     if path != "tile":
         pytest.skip("tile configurations only exist on the tile path")
-    dtype = torch.float32 if cfg < 4 else torch.float64
-    tag = "f32" if cfg < 4 else "f64"
+    dtype = torch.float64 if cfg in (4, 5, 6) else torch.float32
+    tag = "f64" if cfg in (4, 5, 6) else "f32"
     monkeypatch.setenv("NOC_FORCE_CFG", str(cfg))
     c = load_cases("swap12")
     net, prob, xinit, meta = product_setup("swap12", dtype)
     xb = torch.from_numpy(c["xb"]).to(dtype).cuda()
-    got = _three_modes(nb, xb, net, prob, [0.0, 1.0], int(c["nt_batch"]), "rk4", meta["alph"])
-    _compare(tag, 24, got, (c["b_mean_" + tag], c["b_nomean_" + tag], c["b_z_" + tag], c["b_ctrl_" + tag]), "swap12 cfg %d" % cfg)
+    try:
+        got = _three_modes(nb, xb, net, prob, [0.0, 1.0], int(c["nt_batch"]), "rk4", meta["alph"])
+        _compare(tag, 24, got, (c["b_mean_" + tag], c["b_nomean_" + tag], c["b_z_" + tag], c["b_ctrl_" + tag]), "swap12 cfg %d" % cfg)
+    except nb._cabi.NocError as e:
+        assert "noc error -4" in str(e)            # swap12 does not fit this forced tiling (m = 32 on the m <= 16 tile): loud
     # deep / odd-sized net through the same tiling
     z = np.load(GOLDEN + "/phi_random.npz")
     for idx in (1, 2, 3, 4):
