@@ -122,6 +122,28 @@ __device__ __forceinline__ real tanh_only(real pre) {
     return copysign(r_div(real(1) - e, real(1) + e), pre);
 }
 
+#ifndef NOC_PRECISE_MATH
+// fp32 fast path: the three transcendentals as bare MUFU ops (ex2 / lg2 / rcp .approx.ftz).  The library intrinsics
+// wrap each of them in range fix-ups (denormal results of exp, denormal arguments of log, huge divisors) that cannot
+// occur here -- e = exp(-2|x|) is in [0,1], 1+e in [1,2] -- and those fix-ups doubled the size of the activation
+// epilogues, which matters because one stage's code has to stay resident in the instruction cache.
+__device__ __forceinline__ float mufu_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float mufu_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+template <>
+__device__ __forceinline__ void act_tanh<float>(float pre, float& act, float& th) {
+    const float a = fabsf(pre);
+    const float e = mufu_ex2(a * -2.885390081777927f);               // exp(-2a) = 2^(-2 a log2(e))
+    act = fmaf(mufu_lg2(1.0f + e), 0.6931471805599453f, a);          // a + ln(1 + e)
+    th = copysignf((1.0f - e) * mufu_rcp(1.0f + e), pre);
+}
+template <>
+__device__ __forceinline__ float tanh_only<float>(float pre) {
+    const float e = mufu_ex2(fabsf(pre) * -2.885390081777927f);
+    return copysignf((1.0f - e) * mufu_rcp(1.0f + e), pre);
+}
+#endif
+
 // ------------------------------------------------------------------------------------------------
 // 16-byte vector access
 // ------------------------------------------------------------------------------------------------
