@@ -42,6 +42,13 @@ WORKLOADS = {
 }
 
 
+# DRAM bytes per sample of the rollout kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
+# capture, divided by the samples of that launch): profiles/r01_<workload>_ncu_summary.txt.  The algorithmic figure is
+# 4 d bytes per sample (the initial state is read once; mean mode writes nothing per sample).
+DRAM_BYTES_PER_SAMPLE = {"swap12": (12.838656e6 + 1.28e6) / 131072, "swarm50": (14.534144e6 + 1.083904e6) / 16384,
+                         "singlequad": (6.871808e6 + 294.912e6) / 131072}
+
+
 def flops_per_sample_step(d, m, nTh, r):
     D = d + 1
     return 4 * (4 * m * D + 4 * m * m * (nTh - 1) + min(2 * D * D, 4 * r * D))
@@ -349,7 +356,10 @@ def main():
                     "d2h_bytes_per_step": 64},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": ach / peak,
+                         "traffic": (DRAM_BYTES_PER_SAMPLE[args.workload] * n if args.workload in DRAM_BYTES_PER_SAMPLE else None),
+                         "traffic_note": "DRAM bytes per launch = measured bytes per sample of the ncu capture in profiles/ x samples; "
+                                         "algorithmic = %d bytes (4 d per sample)" % (4 * d * n),
                          "peak_source": "measured live: register-resident FMA micro-benchmark on all SMs (noc_measure_fma_peak); "
                                         "MEASURED_PEAKS.json has no FP32/FP64 FMA figure"},
         }

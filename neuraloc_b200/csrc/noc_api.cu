@@ -226,7 +226,7 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
         const int slab = ci.GRP * ci.WB;
         sp.ring_slab = slab; sp.ring_ns = ns;
         // prefer the deeper ring; at equal depth keep the augmented state in shared memory
-        long score = (long)std::min(ns, 6) * 2 + (zg == 0 ? 1 : 0);
+        long score = (long)std::min(ns, 4) * 2 + (zg == 0 ? 1 : 0);     // 4 groups in flight cover the L2 latency
         if (score > best_score) { best_score = score; best = sp; best_bytes = panel_bytes + (size_t)ns * per_group; }
     }
     if (best_score < 0) return 0;
