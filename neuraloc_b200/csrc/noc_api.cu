@@ -119,6 +119,73 @@ static __global__ void __launch_bounds__(32 * WARPS) fma_tile_peak_kernel(float*
     if (s == 123456789.f) out[blockIdx.x * blockDim.x + tid] = s;
 }
 
+// Blackwell packed FP32: one FFMA2 instruction performs two FMAs per lane (fma.rn.f32x2, sm_100+), and accepts a scalar
+// operand broadcast to both halves.  The two kernels below measure what it buys: the dependent-chain peak and the 8x8
+// register-tile inner loop with sample pairs packed.
+static __global__ void __launch_bounds__(256) ffma2_peak_kernel(float* out, int iters, float a, float b) {
+    float2 acc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = make_float2(float(threadIdx.x + i), float(i));
+    const float2 a2 = make_float2(a, a * 1.0000001f), b2 = make_float2(b, b);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int rep = 0; rep < 8; ++rep)
+#pragma unroll
+            for (int i = 0; i < 16; ++i) acc[i] = __ffma2_rn(acc[i], a2, b2);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += acc[i].x + acc[i].y;
+    if (s == 123456789.f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int WARPS>
+static __global__ void __launch_bounds__(32 * WARPS) ffma2_tile_peak_kernel(float* out, int ksteps) {
+    extern __shared__ __align__(16) unsigned char peak_smem[];
+    float* sm = reinterpret_cast<float*>(peak_smem);
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < 64 * 64 * 2; i += 32 * WARPS) sm[i] = 1.0f + 1e-6f * (i & 63);
+    __syncthreads();
+    const float* W = sm + (lane & 7) * 4;
+    const float* Ain = sm + 64 * 64 + (lane >> 3) * 8;
+    float2 acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = make_float2(0.f, 0.f);
+    float w[2][8];
+    float2 a[2][4];
+    auto ldw = [&](int k, float (&v)[8]) {
+        float4 t0 = *reinterpret_cast<const float4*>(W + (k & 63) * 64);
+        float4 t1 = *reinterpret_cast<const float4*>(W + (k & 63) * 64 + 32);
+        v[0] = t0.x; v[1] = t0.y; v[2] = t0.z; v[3] = t0.w; v[4] = t1.x; v[5] = t1.y; v[6] = t1.z; v[7] = t1.w;
+    };
+    auto lda = [&](int k, float2 (&v)[4]) {
+        float4 t0 = *reinterpret_cast<const float4*>(Ain + (k & 63) * 64);
+        float4 t1 = *reinterpret_cast<const float4*>(Ain + (k & 63) * 64 + 4);
+        v[0] = make_float2(t0.x, t0.y); v[1] = make_float2(t0.z, t0.w); v[2] = make_float2(t1.x, t1.y); v[3] = make_float2(t1.z, t1.w);
+    };
+    ldw(0, w[0]); lda(0, a[0]);
+    for (int k = 0; k < ksteps; k += 2) {
+        ldw(k + 1, w[1]); lda(k + 1, a[1]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(w[0][i], w[0][i]), a[0][j], acc[i][j]);
+        ldw(k + 2, w[0]); lda(k + 2, a[0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = __ffma2_rn(make_float2(w[1][i], w[1][i]), a[1][j], acc[i][j]);
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) s += acc[i][j].x + acc[i][j].y;
+    if (s == 123456789.f) out[blockIdx.x * blockDim.x + tid] = s;
+}
+
 struct CfgInfo {
     int id, PB, WB, NWO, TS, TSP, NT, TPS, GRP;
     bool wsmem, zglobal;
@@ -596,6 +663,52 @@ int noc_measure_fma_peak(int32_t dtype, double* tflops) {
     if (!tflops) return fail(NOC_ERR_ARG, "tflops is NULL");
     int rc = device_facts();
     if (rc) return rc;
+    if (dtype == 4) {                    // packed FFMA2 dependent-chain peak
+        const int blocks = g_sm_count * 8, threads = 256, iters = 16384;
+        void* o = nullptr;
+        NOC_CUDA(cudaMalloc(&o, (size_t)blocks * threads * 4));
+        cudaEvent_t a0, a1;
+        NOC_CUDA(cudaEventCreate(&a0));
+        NOC_CUDA(cudaEventCreate(&a1));
+        float bestms = 1e30f;
+        for (int rep = 0; rep < 4; ++rep) {
+            NOC_CUDA(cudaEventRecord(a0));
+            ffma2_peak_kernel<<<blocks, threads>>>((float*)o, iters, 1.0000001f, 1e-9f);
+            count_launch();
+            NOC_CUDA(cudaEventRecord(a1));
+            NOC_CUDA(cudaEventSynchronize(a1));
+            float ms = 0;
+            NOC_CUDA(cudaEventElapsedTime(&ms, a0, a1));
+            if (rep > 0) bestms = std::min(bestms, ms);
+        }
+        *tflops = 2.0 * 2 * 16 * 8 * (double)iters * blocks * threads / (bestms * 1e-3) / 1e12;
+        cudaEventDestroy(a0); cudaEventDestroy(a1); cudaFree(o);
+        return NOC_OK;
+    }
+    if (dtype == 5 || dtype == 6) {      // 8x8 register-tile inner loop with packed FFMA2 at 8 / 16 warps per SM
+        const int ksteps = 1 << 15, smem = 64 * 64 * 2 * 4;
+        void* o = nullptr;
+        NOC_CUDA(cudaMalloc(&o, (size_t)g_sm_count * 512 * 4));
+        cudaEvent_t a0, a1;
+        NOC_CUDA(cudaEventCreate(&a0));
+        NOC_CUDA(cudaEventCreate(&a1));
+        float bestms = 1e30f;
+        for (int rep = 0; rep < 3; ++rep) {
+            NOC_CUDA(cudaEventRecord(a0));
+            if (dtype == 5) ffma2_tile_peak_kernel<8><<<g_sm_count, 256, smem>>>((float*)o, ksteps);
+            else ffma2_tile_peak_kernel<16><<<g_sm_count, 512, smem>>>((float*)o, ksteps);
+            count_launch();
+            NOC_CUDA(cudaEventRecord(a1));
+            NOC_CUDA(cudaEventSynchronize(a1));
+            float ms = 0;
+            NOC_CUDA(cudaEventElapsedTime(&ms, a0, a1));
+            if (rep > 0) bestms = std::min(bestms, ms);
+        }
+        const double thr = (dtype == 5) ? 256.0 : 512.0;
+        *tflops = 2.0 * 64 * (double)ksteps * g_sm_count * thr / (bestms * 1e-3) / 1e12;
+        cudaEventDestroy(a0); cudaEventDestroy(a1); cudaFree(o);
+        return NOC_OK;
+    }
     if (dtype == 2 || dtype == 3) {      // inner-loop ceiling of the 8x8 register tile at 8 / 16 resident warps per SM
         const int ksteps = 1 << 15, smem = 64 * 64 * 2 * 4;
         void* o = nullptr;
