@@ -1,9 +1,9 @@
-// noc_api.cu — C ABI (include/noc_b200.h) over the persistent rollout kernel.
+// noc_api.cu — C ABI (include/noc_b200.h) over the rollout kernels.
 //
-// Host-side work per call: pick a tile configuration for (dtype, m, D), lay out the shared-memory
-// panels, pack the value-network weights into the K-major permuted blob the kernel reads (a tiny
-// kernel, stream-ordered), launch ONE rollout kernel + a 1-block finishing reduction.  All scratch is
-// stream-ordered (cudaMallocAsync), so calls on different streams do not interfere.
+// Host-side work per call: pick the path (small batches -> noc_vec.cu, otherwise a tile configuration for
+// (dtype, m, D)), lay out the shared-memory panels, pack the value-network weights into the K-major blob the
+// kernel reads (a tiny kernel, stream-ordered), launch ONE rollout kernel + a 1-block finishing reduction.
+// All scratch is stream-ordered (cudaMallocAsync), so calls on different streams do not interfere.
 #include <cuda_runtime.h>
 
 #include <algorithm>

@@ -1,18 +1,19 @@
-// noc_rollout.cuh — the persistent rollout kernel (FP32 / FP64 FMA register tiles).
+// noc_rollout.cuh — the persistent sample-tile rollout kernel (FP32 / FP64 FMA register tiles).
 //
 // One launch integrates a whole OCflow call (src/OCflow.py:7-95).  A CTA owns a tile of TS samples for
-// all nt steps: the augmented state z = [x, L, HJt, Q, W] and every hidden vector of Phi live in shared
-// memory as [unit][sample] panels (sample contiguous), each Phi contraction is a register-tiled
-// FMA GEMM (RO outputs x RS samples per thread) whose epilogue applies the activation in registers, and
-// the problem terms (Cross2D / SwarmTraj / Quadcopter) are evaluated per sample between contractions.
-// Nothing but the initial state is read from HBM and nothing but the costs (or, with
-// intermediates=True, the trajectory) is written.
+// all nt steps: every hidden vector of Phi lives in shared memory as [unit][sample] panels (sample
+// contiguous), each Phi contraction is a register-tiled FMA GEMM (RO outputs x RS samples per thread;
+// fp32 uses Blackwell's packed FFMA2) whose epilogue applies the activation in registers, and the problem
+// terms (Cross2D / SwarmTraj / Quadcopter) are evaluated per sample between contractions.  Nothing but the
+// initial state is read from HBM and nothing but the costs (or, with intermediates=True, the trajectory) is
+// written.  Weights: the whole packed blob staged in shared memory (small nets) or streamed through
+// warp-private cp.async rings (m >= 128).  DESIGN.md §3 has the configuration table and the measurements.
 //
 // Per ODE-function evaluation (ocOdefun, OCflow.py:104-140; Phi.getGrad, Phi.py:99-138), nTh = 2:
 //   GEMM-1  o  = K0 s + b0        ->  u0 = act(o) (panel U), t0 = tanh(o) (panel T0)
 //   GEMM-2  a1 = K1 u0 + b1       ->  y  = tanh(a1) * w           (U, in place)
 //   GEMM-3  z1 = w + h K1' y      ->  v  = t0 * z1                (U, in place)
-//   GEMM-4  g  = K0' v + A'A s + c_w                              (panel G)
+//   GEMM-4  g  = A'A s + K0' v + c_w                              (panel G)
 // then L, H, Q, W from (x, p = g[:d]) and the RK combination.  General nTh keeps tanh(a_i) panels.
 #pragma once
 #include <cuda_runtime.h>
@@ -164,22 +165,6 @@ __device__ __forceinline__ void ld_panel(const double* p, double (&v)[N]) {
     }
 }
 template <int N>
-__device__ __forceinline__ void ld_weights_global(const float* p, float (&v)[N]) {
-#pragma unroll
-    for (int i = 0; i < N / 4; ++i) {
-        float4 t = __ldg(reinterpret_cast<const float4*>(p + 4 * i));
-        v[4 * i] = t.x; v[4 * i + 1] = t.y; v[4 * i + 2] = t.z; v[4 * i + 3] = t.w;
-    }
-}
-template <int N>
-__device__ __forceinline__ void ld_weights_global(const double* p, double (&v)[N]) {
-#pragma unroll
-    for (int i = 0; i < N / 2; ++i) {
-        double2 t = __ldg(reinterpret_cast<const double2*>(p + 2 * i));
-        v[2 * i] = t.x; v[2 * i + 1] = t.y;
-    }
-}
-template <int N>
 __device__ __forceinline__ void st_panel(float* p, const float (&v)[N]) {
 #pragma unroll
     for (int i = 0; i < N / 4; ++i)
@@ -234,7 +219,7 @@ struct ThreadMap {
 struct Panels {
     int U, U2, T[MAXL], Zb, S, G, Qs, Z0, ZA, SC, RED, PN, QX, GP;
     int W;            // staged weight blob (WSMEM configurations) / slab ring (streamed configurations)
-    int ring_slab, ring_ns;
+    int ring_slab, ring_ns;   // elements per ring slot (GRP rows of WB columns), slots per warp
     unsigned smem_u32;   // shared-window address of the dynamic shared-memory base (cp.async destinations)
 };
 

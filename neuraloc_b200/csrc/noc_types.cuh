@@ -29,10 +29,10 @@ struct PhiPack {
     int blob_len;
     // The weight matrices in the order one grad-Phi evaluation consumes them (W1, Kf_1.., Kr_nTh-1..1, sym, W4):
     // they are laid out contiguously in that order, so a streamed configuration prefetches "the next slab" without
-    // caring about matrix boundaries (noc_rollout.cuh: WStream).
+    // caring about contraction or stage boundaries (noc_rollout.cuh: WStream).
     int nseq;
     int seq_off[2 * MAXL + 1], seq_N[2 * MAXL + 1], seq_K[2 * MAXL + 1];
-    int ntile_d, ksplit;       // D-wide contractions (sym, W4) in streamed configs: warp tiles across outputs x K-split
+    int ntile_d, ksplit;       // D-wide contractions (sym, W4) in streamed configs: output tiles, and the most K-slices a tile gets
 };
 
 // Raw (reference-layout) pointers handed to the pack kernel.
@@ -65,8 +65,8 @@ struct SmemPlan {
     int QX;                    // Quadcopter per-agent scalars [5 * nAgents]: u/mass, f7, f8, f9, u
     int GP;                    // partial sums of the K-split D-wide contractions (streamed configs)
     int rows;                  // total rows
-    int wsm_off;               // element offset of the weight blob copy (WSMEM configs) / of the slab ring (streamed)
-    int ring_slab, ring_ns;    // streamed configs: elements per ring slot, number of slots (2..4)
+    int wsm_off;               // element offset of the weight blob copy (WSMEM configs) / of the warps' rings (streamed)
+    int ring_slab, ring_ns;    // streamed configs: elements per ring slot (GRP rows x WB columns), slots per warp (2..8)
     int z_global;              // Z0/ZA live in a per-CTA global scratch instead of shared memory
 };
 

@@ -71,10 +71,16 @@ __global__ void pack_phi_plain_kernel(const PhiRaw<real> R, const VecPack<real> 
 }
 
 // deterministic block-wide sum: every thread returns the same total (fixed shuffle tree + fixed warp order)
-template <typename real>
+template <bool ONEWARP>
+__device__ __forceinline__ void cta_sync() {
+    if (ONEWARP) __syncwarp(); else __syncthreads();
+}
+
+template <typename real, bool ONEWARP>
 __device__ __forceinline__ real block_sum(real v, real* red, int tid, int nthreads) {
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    if (ONEWARP) return v;                 // nets with m, d+4 <= 32 run as a single warp: no shared-memory stage
     __syncthreads();                       // previous users of `red` are done
     if ((tid & 31) == 0) red[tid >> 5] = v;
     __syncthreads();
@@ -99,7 +105,7 @@ __device__ __forceinline__ real gemv_col(const real* __restrict__ W, int N, cons
     return (a0 + a1) + (a2 + a3);
 }
 
-template <typename real, bool WSM>
+template <typename real, bool WSM, bool ONEWARP>
 __global__ void rollout_vec_kernel(const VecArgs<real> A) {
     extern __shared__ __align__(16) unsigned char vec_smem[];
     real* sm = reinterpret_cast<real*>(vec_smem);
@@ -115,7 +121,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
         for (int i = tid; i < P.blob_len; i += NT) sm[A.o_w + i] = P.blob[i];
     }
     const real* wb = WSM ? (sm + A.o_w) : P.blob;
-    __syncthreads();
+    cta_sync<ONEWARP>();
 
     // grad Phi (Phi.py:99-138) of the s = [x,t] in `s` -> g; terminal also Phi's pieces: returns w . u_last
     auto chain = [&](bool terminal) -> real {
@@ -129,7 +135,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
             u[tid] = av;
             tbuf[tid] = tv;
         }
-        __syncthreads();
+        cta_sync<ONEWARP>();
         for (int i = 1; i < nTh; ++i) {              // forward layers (Phi.py:118-120)
             const bool last = (i == nTh - 1);
             real part = real(0);
@@ -152,8 +158,8 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                     }
                 }
             }
-            if (terminal && last) phiN = block_sum(part, red, tid, NT);
-            __syncthreads();
+            if (terminal && last) phiN = block_sum<real, ONEWARP>(part, red, tid, NT);
+            cta_sync<ONEWARP>();
             real* t = u; u = u2; u2 = t;
         }
         for (int i = nTh - 1; i >= 1; --i) {         // reverse sweep (Phi.py:124-131); u holds y
@@ -163,7 +169,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                 if (i > 1) zbv[tid] = zi;
                 u2[tid] = tbuf[(i - 1) * m + tid] * zi;
             }
-            __syncthreads();
+            cta_sync<ONEWARP>();
             real* t = u; u = u2; u2 = t;
         }
         if (tid < D) {                               // grad = A'A s + K0' v + c_w' (Phi.py:133-136)
@@ -171,7 +177,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
             if (terminal) qv[tid] = q;
             g[tid] = (q + gemv_col<real, WSM>(wb + P.off_W4 + tid, D, u, m)) + wb[P.off_cw + tid];
         }
-        __syncthreads();
+        cta_sync<ONEWARP>();
         return phiN;
     };
 
@@ -208,17 +214,17 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                 }
                 sc[SC_L] = L; sc[SC_HJ] = r_abs(g[d] - H); sc[SC_Q] = Q; sc[SC_W] = W;
             }
-            __syncthreads();
+            cta_sync<ONEWARP>();
             return;
         }
         const int Ag = pr.nAgents, dim = pr.agentDim;
-        real pp = block_sum((tid < d) ? g[tid] * g[tid] : real(0), red, tid, NT);
+        real pp = block_sum<real, ONEWARP>((tid < d) ? g[tid] * g[tid] : real(0), red, tid, NT);
         real q = real(0), w = real(0);
         const bool needQ = (pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0);
         if (needQ) {
             real mine = real(0);
             for (int a = tid; a < Ag; a += NT) mine += terrain_agent<real>(pr, s[a * dim], s[a * dim + 1], dim == 3 ? s[a * dim + 2] : real(0));
-            q = block_sum(mine, red, tid, NT);
+            q = block_sum<real, ONEWARP>(mine, red, tid, NT);
         }
         if (pr.alph_W != 0.0 && Ag >= 2) {
             const real cut = real(pr.cutW), c2 = real(2 * pr.r * pr.r);
@@ -236,7 +242,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                     if (Ag == 2 || e != real(1)) mine += e;     // the "== 1" rule applies to the A > 2 branch only
                 }
             }
-            w = block_sum(mine, red, tid, NT);
+            w = block_sum<real, ONEWARP>(mine, red, tid, NT);
         }
         if (tid == 0) {
             real Qret, L;
@@ -246,7 +252,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
             real H = -L + pp;
             sc[SC_L] = L; sc[SC_HJ] = r_abs(g[d] - H); sc[SC_Q] = Qret; sc[SC_W] = w;
         }
-        __syncthreads();
+        cta_sync<ONEWARP>();
     };
     auto rate = [&](int row) -> real {               // dx/dt = -grad_p H
         if (pr.kind != 2) return -g[row];
@@ -267,7 +273,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
     for (long long smp = blockIdx.x; smp < A.n; smp += gridDim.x) {
         if (tid < d) z0[tid] = A.x[smp * d + tid];
         else if (tid < d + 4) z0[tid] = real(0);
-        __syncthreads();
+        cta_sync<ONEWARP>();
         if (inter) {
             if (tid < d + 4) A.out_b[(smp * (d + 4) + tid) * ntp1] = z0[tid];
             for (int c = tid; c < pr.nctrl; c += NT) A.out_c[(smp * pr.nctrl + c) * ntp1] = real(0);
@@ -278,7 +284,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
             if (nstage > 0) {
                 if (tid < d) s[tid] = z0[tid];
                 if (tid == d) s[d] = real(tt[0]);
-                __syncthreads();
+                cta_sync<ONEWARP>();
             }
             for (int st = 0; st < nstage; ++st) {
                 real wgt, cnext, tnext;
@@ -295,37 +301,37 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                     kk = hstep * ((tid < d) ? rate(tid) : sc[tid - d]);
                     z0v = z0[tid];
                 }
-                __syncthreads();                     // every rate() has read s before s is rewritten
+                cta_sync<ONEWARP>();                     // every rate() has read s before s is rewritten
                 if (tid < d + 4) {
                     za[tid] = ((st == 0) ? z0v : za[tid]) + wgt * kk;
                     if (!lastst && tid < d) s[tid] = z0v + cnext * kk;
                 }
                 if (!lastst && tid == d) s[d] = tnext;
-                __syncthreads();
+                cta_sync<ONEWARP>();
             }
             if (nstage > 0) { real* t = z0; z0 = za; za = t; }
             if (inter) {
                 if (tid < d + 4) A.out_b[(smp * (d + 4) + tid) * ntp1 + (k + 1)] = z0[tid];
                 if (tid < d) s[tid] = z0[tid];
                 if (tid == d) s[d] = real(tt[3]);
-                __syncthreads();
+                cta_sync<ONEWARP>();
                 chain(false);
                 if (pr.kind == 2) problem();
                 for (int c = tid; c < pr.nctrl; c += NT) A.out_c[(smp * pr.nctrl + c) * ntp1 + (k + 1)] = control(c);
-                __syncthreads();
+                cta_sync<ONEWARP>();
             }
         }
         // terminal block (OCflow.py:58-90)
         if (tid < d) s[tid] = z0[tid];
         if (tid == d) s[d] = A.t_end;
-        __syncthreads();
+        cta_sync<ONEWARP>();
         const real phiN = chain(true);
         const real* xt = static_cast<const real*>(pr.xtarget);
         real res = (tid < d) ? (z0[tid] - xt[tid]) : real(0);
-        real cG = real(0.5) * block_sum(res * res, red, tid, NT);
-        real hjg = block_sum((tid < d) ? r_abs(g[tid] - A.alph0 * res) : real(0), red, tid, NT);
-        real quad = block_sum((tid < D) ? s[tid] * qv[tid] : real(0), red, tid, NT);
-        real lin = block_sum((tid < D) ? wb[P.off_cw + tid] * s[tid] : real(0), red, tid, NT);
+        real cG = real(0.5) * block_sum<real, ONEWARP>(res * res, red, tid, NT);
+        real hjg = block_sum<real, ONEWARP>((tid < d) ? r_abs(g[tid] - A.alph0 * res) : real(0), red, tid, NT);
+        real quad = block_sum<real, ONEWARP>((tid < D) ? s[tid] * qv[tid] : real(0), red, tid, NT);
+        real lin = block_sum<real, ONEWARP>((tid < D) ? wb[P.off_cw + tid] * s[tid] : real(0), red, tid, NT);
         if (tid == 0) {
             real phi1 = phiN + real(0.5) * quad + (lin + wb[P.off_cb]);
             real c[7] = {z0[d], cG, z0[d + 1], r_abs(phi1 - A.alph0 * cG), hjg, z0[d + 2], z0[d + 3]};
@@ -338,7 +344,7 @@ __global__ void rollout_vec_kernel(const VecArgs<real> A) {
                 for (int q = 0; q < 7; ++q) o[1 + q] = c[q];
             }
         }
-        __syncthreads();
+        cta_sync<ONEWARP>();
     }
 }
 
@@ -363,7 +369,7 @@ int vec_rollout(int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw,
     // shared-memory vectors
     int so = 0;
     auto stake = [&](int cnt) { int o = so; so += align_up(cnt, 8); return o; };
-    const int nthreads = std::min(1024, std::max(64, align_up(std::max(std::max(m, D), d + 4), 32)));
+    const int nthreads = std::min(1024, std::max(32, align_up(std::max(std::max(m, D), d + 4), 32)));
     A.o_s = stake(D); A.o_u = stake(m); A.o_u2 = stake(m); A.o_t = stake(std::max(1, nTh - 1) * m); A.o_zb = stake(m);
     A.o_g = stake(D); A.o_q = stake(D); A.o_z0 = stake(d + 4); A.o_za = stake(d + 4); A.o_sc = stake(8); A.o_red = stake(32);
     A.o_qx = stake(5 * std::max(1, pr.nAgents)); A.o_w = so;
@@ -387,7 +393,9 @@ int vec_rollout(int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw,
         NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)n, st));
         A.partials = partials;
     }
-    auto kern = wsm ? rollout_vec_kernel<real, true> : rollout_vec_kernel<real, false>;
+    const bool onewarp = wsm && nthreads == 32;
+    auto kern = onewarp ? rollout_vec_kernel<real, true, true>
+                        : (wsm ? rollout_vec_kernel<real, true, false> : rollout_vec_kernel<real, false, false>);
     NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int grid = (int)std::min<long long>(n, 16LL * sm_count());
     kern<<<grid, nthreads, smem, st>>>(A);
