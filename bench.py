@@ -214,6 +214,38 @@ def latency_mode(args, W, dtype, threads):
     return line
 
 
+def intermediates_mode(args, W, dtype):
+    """OCflow(..., intermediates=True) on a device-resident batch: zFull [n,d+4,nt+1] and ctrlFull [n,nCtrl,nt+1] are written
+    to HBM (5 grad-Phi evaluations per step instead of 4).  Reports sample-steps/s and the output bandwidth."""
+    import neuraloc_b200 as nb
+    nb._cabi.lib()
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    n, nt = (args.n or min(W["n"], 1 << 18)), W["nt"]
+    net, prob, xinit, meta = build_case(args.workload, device, dtype)
+    x = sample_x(args.workload, xinit, meta["var0"], n, 1234, device, dtype)
+    with torch.no_grad():
+        for _ in range(max(1, args.warmup)):
+            zf, cf = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        torch.cuda.synchronize()
+        ms = []
+        for _ in range(args.steps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            zf, cf = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+            e1.record()
+            torch.cuda.synchronize()
+            ms.append(e0.elapsed_time(e1))
+    out_bytes = (zf.numel() + cf.numel()) * zf.element_size()
+    t = statistics.mean(ms) * 1e-3
+    return {"metric": "rk4_sample_steps_per_sec_intermediates", "value": n * nt / t, "unit": "sample-steps/s", "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": statistics.mean(ms), "dtype": W["dtype"],
+            "config": {"workload": "%s, intermediates=True, %d samples, nt=%d" % (args.workload, n, nt)},
+            "output_bytes": out_bytes, "output_GBps": out_bytes / t / 1e9,
+            "roofline": {"bound": "hbm", "achieved": out_bytes / t / 1e9, "peak": 6539.2, "unit": "GB/s", "frac": out_bytes / t / 1e9 / 6539.2,
+                         "note": "peak = MEASURED_PEAKS.json hbm_gbs; this mode is still compute-bound at these sizes"}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -224,6 +256,7 @@ def main():
     ap.add_argument("--samples", dest="n", type=int, default=0, help="samples per GPU (default: the workload's)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--latency", action="store_true", help="batch-1 rollout latency (timeDeployment/timeOC.py protocol) instead of throughput")
+    ap.add_argument("--intermediates", action="store_true", help="time OCflow(..., intermediates=True): trajectories + controls written to HBM (SURVEY.md 8f N2)")
     args = ap.parse_args()
     W = WORKLOADS[args.workload]
     n = args.n or W["n"]
@@ -257,6 +290,9 @@ def main():
 
     if args.latency:
         print(json.dumps(latency_mode(args, W, dtype, threads)))
+        return
+    if args.intermediates:
+        print(json.dumps(intermediates_mode(args, W, dtype)))
         return
 
     # ------------------------------------------------------------------ our arm

@@ -1,0 +1,159 @@
+"""More GPU coverage: randomized problem functors against the oracle (all thread decompositions), the drop-in import hook
+driving an evalOC-style script end to end, intermediates at a size that spans many tiles, and size-independent properties
+at benchmark-scale batches."""
+import json
+import os
+import subprocess
+import sys
+import textwrap
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import ROOT, check_costs, load_cases, product_setup, rel_err, rel_state_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def nb():
+    import neuraloc_b200
+    neuraloc_b200._cabi.lib()
+    return neuraloc_b200
+
+
+@pytest.mark.parametrize("cfg", [None, 2, 3, 5, 6])
+@pytest.mark.parametrize("name", ["softcorridor", "swap2", "swap12", "midcross4", "swarm50", "swarm", "singlequad"])
+def test_randomized_functors_vs_oracle(nb, name, cfg, monkeypatch):
+    """calcLHQW / calcGradpH / calcCtrls on 300 random (x, p) rows, eval and train mode, through the one-thread-per-sample
+    decomposition (default) and the split-across-threads ones (forced mid / large tiles)."""
+    from oracle import ocflow_oracle as orc
+    dtype = torch.float64 if cfg in (5, 6) else torch.float32
+    if cfg is not None:
+        monkeypatch.setenv("NOC_FORCE_CFG", str(cfg))
+    alph = [300.0, 2.5, 7.0, 1.0, 1.0, 1.0] if name != "singlequad" else [5000.0, 0.0, 0.0, 0.1, 0.0, 0.0]
+    prob, _, _, xinit = nb.initProb(name, 2, 2, 1.0, alph, lambda v: v.to(dtype).cuda())
+    D, _ = orc.make_problem(name, alph, torch.float64)
+    g = torch.Generator().manual_seed(sum(map(ord, name)))
+    n, d = 300, xinit.shape[1]
+    x = xinit.cpu() + 0.7 * torch.randn(n, d, generator=g, dtype=dtype)
+    p = 1.5 * torch.randn(n, d, generator=g, dtype=dtype)
+    if prob.nAgents >= 2 and name != "singlequad":       # squeeze some agents together so that W is exercised
+        A, dim = prob.nAgents, prob.agentDim
+        xa = x.view(n, A, dim).clone()
+        xa[: n // 3, 1] = xa[: n // 3, 0] + prob.r * torch.rand(n // 3, dim, generator=g, dtype=dtype) * 1.5
+        x = xa.reshape(n, d)
+    tol = 2e-5 if dtype == torch.float32 else 1e-11
+    for mode in ("eval", "train"):
+        getattr(prob, mode)()
+        D.training = (mode == "train")
+        try:
+            L, H, Q, W = prob.calcLHQW(x.cuda(), p.cuda())
+        except nb._cabi.NocError as e:               # e.g. d = 150 does not fit the forced 2-warp-wide tiling: loud
+            assert cfg is not None and "noc error -4" in str(e)
+            pytest.skip("problem does not fit forced configuration %s" % cfg)
+        Lr, Hr, Qr, Wr = orc.lhqw(D, x.double(), p.double())
+        for got, ref, nm in ((L, Lr, "L"), (H, Hr, "H"), (Q, Qr, "Q"), (W, Wr, "W")):
+            ref = ref.reshape(-1).numpy() if torch.is_tensor(ref) else np.zeros(n)
+            got = got.reshape(-1).cpu().numpy()
+            # a pair (or an agent) within rounding of a cut-off can land on either side in fp32: allow two such rows
+            err = np.abs(got - ref) / np.maximum(np.abs(ref), 1.0)
+            assert (err > tol).sum() <= (2 if dtype == torch.float32 else 0), (name, mode, nm, cfg, err.max())
+        assert rel_err(prob.calcGradpH(x.cuda(), p.cuda()).cpu().numpy(),
+                       orc.grad_p_hamiltonian(D, x.double(), p.double()).numpy(), floor=1.0) <= tol
+        assert rel_err(prob.calcCtrls(x.cuda(), p.cuda()).cpu().numpy(),
+                       orc.controls(D, x.double(), p.double()).numpy(), floor=1.0) <= tol
+
+
+def test_dropin_hook_runs_an_evalOC_style_script(nb, tmp_path):
+    """INTEGRATION.md §1 without the reference checkout (absent on the GPU box): a stand-in `src` package whose OCflow
+    must never run, the sitecustomize hook first on PYTHONPATH, and a script written like evalOC.py:51-85."""
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "__init__.py").write_text("")
+    (src / "OCflow.py").write_text(textwrap.dedent("""
+        def OCflow(*a, **k):
+            raise AssertionError("the stand-in reference OCflow ran: the drop-in hook did not rebind it")
+        stepRK4 = stepRK1 = ocOdefun = OCflow
+        def ocG(z, xtarget):
+            return z[:, :xtarget.shape[0]] - xtarget
+    """))
+    script = tmp_path / "eval_like.py"
+    script.write_text(textwrap.dedent("""
+        import sys, json, torch
+        sys.path.insert(0, %r)
+        from src.OCflow import OCflow                 # what evalOC.py:9 does
+        from helpers import load_ckpt
+        import neuraloc_b200 as nb
+        sd, meta = load_ckpt("softcorridor")
+        cvt = lambda v: v.type(torch.float32).to("cpu")          # evalOC.py is CPU-only (F2)
+        prob, x0, _, xInit = nb.initProb(meta["data"], 10, 11, var0=1.0, alph=meta["alph"], cvt=cvt)
+        prob.eval()
+        net = nb.Phi(nTh=meta["nTh"], m=meta["m"], d=x0.size(1), alph=meta["alph"])
+        net.load_state_dict(sd)
+        with torch.no_grad():
+            Jc, cs = OCflow(xInit, net, prob, tspan=[0.0, 1.0], nt=50, stepper="rk4", alph=net.alph)
+            zFull, ctrlFull = OCflow(xInit, net, prob, tspan=[0.0, 1.0], nt=50, stepper="rk4", alph=net.alph, intermediates=True)
+        print('{:12.4e} {:11.3e}'.format(cs[0] + meta["alph"][0] * cs[1], cs[0]))
+        print("RESULT " + json.dumps([float(Jc)] + [float(c) for c in cs] + [float(zFull[0, :4, -1].norm()), float(ctrlFull[0, :, -1].norm())]))
+    """ % os.path.join(ROOT, "tests")))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "neuraloc_b200", "dropin"), ROOT, str(tmp_path)]))
+    env.pop("NOC_FORCE_PATH", None)
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    vals = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    c = load_cases("softcorridor")
+    check_costs(vals[:8], c["xinit_mean_f32"], 2e-3, 2e-4, "evalOC-style run through the hook")
+    # SURVEY.md §8c known answers: |x(T)| = 3.95163, |u(T)| = 5.23089
+    assert abs(vals[8] - 3.95163178) < 1e-4 and abs(vals[9] - 5.23088646) < 1e-3
+
+
+@pytest.mark.parametrize("name", ["swap12", "singlequad"])
+def test_intermediates_across_many_tiles(nb, name, monkeypatch):
+    """intermediates=True on 3000 samples (several tiles per CTA, ragged last tile): trajectories agree with the small-batch
+    kernel sample by sample, zFull's last column agrees with the noMean costs, controls at step 0 are zero."""
+    net, prob, xinit, meta = product_setup(name, torch.float32)
+    d = xinit.shape[1]
+    g = torch.Generator().manual_seed(4)
+    x = (xinit.cpu() + 0.3 * torch.randn(3000, d, generator=g)).cuda()
+    if name == "singlequad":
+        x[:, 3:] = 0
+    nt = 12
+    with torch.no_grad():
+        monkeypatch.setenv("NOC_FORCE_PATH", "tile")
+        zf, cf = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        Jn, cn = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+        monkeypatch.setenv("NOC_FORCE_PATH", "vec")
+        idx = torch.tensor([0, 1, 479, 480, 481, 1500, 2879, 2880, 2999], device="cuda")
+        zv, cv = nb.OCflow(x[idx].contiguous(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+    assert zf.shape == (3000, d + 4, nt + 1) and not cf[:, :, 0].any()
+    assert rel_state_err(zf[idx].cpu().numpy(), zv.cpu().numpy(), d) <= 2e-6
+    assert (cf[idx] - cv).abs().max() <= 1e-4 * max(1.0, float(cv.abs().max()))
+    assert torch.allclose(zf[:, d, -1:], cn[0], rtol=1e-6, atol=1e-6)          # accumulated L
+    assert torch.allclose(zf[:, d + 1, -1:], cn[2], rtol=1e-6, atol=1e-6)      # accumulated HJt
+
+
+def test_benchmark_scale_properties(nb, monkeypatch):
+    """Size-independent properties at benchmark-like batch sizes (the oracle cannot run there): permutation invariance of
+    the means, additivity of the cost sums over row shards, determinism, and mean == mean of noMean."""
+    monkeypatch.delenv("NOC_FORCE_PATH", raising=False)
+    net, prob, xinit, meta = product_setup("swap12", torch.float32)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    n = 200_000
+    x = xinit + torch.randn(n, 24, generator=g, device="cuda")
+    with torch.no_grad():
+        s_all = nb.ocflow_sums(x, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        s_again = nb.ocflow_sums(x, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        perm = torch.randperm(n, generator=g, device="cuda")
+        s_perm = nb.ocflow_sums(x[perm].contiguous(), net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        lo = nb.ocflow_sums(x[:77_777].contiguous(), net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        hi = nb.ocflow_sums(x[77_777:].contiguous(), net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        Jn, cn = nb.OCflow(x, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"], noMean=True)
+    assert torch.equal(s_all, s_again)                                           # fixed reduction order
+    assert float(s_all[7]) == n
+    assert torch.allclose(s_all, s_perm, rtol=1e-9, atol=1e-6)                   # per-sample results do not depend on the tile
+    assert torch.allclose(s_all, lo + hi, rtol=1e-9, atol=1e-6)                  # shards add (the multi-GPU contract)
+    means = (s_all[:7] / n).cpu().numpy()
+    nm = torch.cat(list(cn), 1).double().mean(0).cpu().numpy()
+    check_costs(means, nm, 1e-6, 1e-7, "mean mode vs mean of noMean")
