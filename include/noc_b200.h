@@ -142,6 +142,13 @@ int noc_prob_eval(const noc_prob_t* prob, const void* x, const void* p, int64_t 
  * FMA micro-benchmark on all SMs. Returns TFLOP/s (2 flops per FMA) in *tflops. Synchronises. */
 int noc_measure_fma_peak(int32_t dtype, double* tflops);
 
+/* Self-test of the Blackwell tensor-core building blocks (tcgen05.mma with TMEM accumulators, no-swizzle shared-memory
+ * descriptors in both majors, tcgen05.ld/st, tcgen05.commit -> mbarrier): one CTA computes D[128,N] = A[128,K] * B in bf16
+ * with fp32 accumulation.  B is [N,K] (b_mn_major = 0) or [K,N] read MN-major (b_mn_major = 1).  All pointers dev.
+ * Diagnostics for the tensor-core rollout path under construction; not used by noc_ocflow. */
+int noc_tc_probe(const void* A_bf16, const void* B_bf16, void* D_f32, int32_t N, int32_t K, int32_t b_mn_major,
+                 int32_t roundtrip_tmem, void* stream);
+
 /* Kernel-launch counter (number of CUDA kernels this library launched in this process); bench.py reports it. */
 int64_t noc_launch_count(void);
 
