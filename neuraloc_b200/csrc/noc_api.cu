@@ -448,6 +448,17 @@ static void stage_times_host(double t0, double t1, int nt, double* tab) {
     }
 }
 
+// the tensor-core kernel exists for fp32 only; the fp64 overload is never selected (use_tc is false) but must compile
+static int tc_launch(int d, int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n,
+                     const double* dt, int nt, int stepper, int mode, const double* alph, double t_end, double* sums, float* a,
+                     float* b, float* c, int lim, cudaStream_t st) {
+    return tc_quad_rollout(d, m, r, h, raw, pr, x, n, dt, nt, stepper, mode, alph, t_end, sums, a, b, c, lim, st);
+}
+static int tc_launch(int, int, int, double, const PhiRaw<double>&, const ProbPack&, const double*, long long, const double*, int, int,
+                     int, const double*, double, double*, double*, double*, double*, int, cudaStream_t) {
+    return fail(NOC_ERR_UNSUPPORTED, "the tensor-core path is fp32 only");
+}
+
 template <typename real>
 static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x, int64_t n, const double* stage_times,
                        double t0, double t1, int nt, int stepper, const double* alph, int mode, void* out_costs,
@@ -480,10 +491,19 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
         else if (!strcmp(e, "tile")) use_vec = false;
     }
     if (std::max(ph->m, ph->d + 4) > 1024) use_vec = false;
+    // tensor-core path (noc_tc_quad.cu) for the shapes it is written for; NOC_TC=0 turns it off, NOC_FORCE_PATH=tc forces it
+    bool use_tc = false;
+    if (std::is_same<real, float>::value && pb->kind == NOC_PROB_QUADCOPTER && pb->nAgents == 1 && ph->d == 12 && ph->nTh == 2 &&
+        ph->m % 16 == 0 && ph->m >= 16 && ph->m <= 128) {
+        const char* tc = getenv("NOC_TC");
+        const char* fp = getenv("NOC_FORCE_PATH");
+        use_tc = (tc && !strcmp(tc, "1") && !use_vec) || (fp && !strcmp(fp, "tc"));
+        if (use_tc) use_vec = false;
+    }
 
     int cfg_id = -1;
     size_t smem = 0;
-    if (!use_vec) {
+    if (!use_vec && !use_tc) {
         rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
         if (rc) return rc;
     }
@@ -500,7 +520,10 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     A.t_end = (real)t1;
     A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
     A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
-    if (use_vec)
+    if (use_tc)
+        rc = tc_launch(ph->d, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph, t1,
+                       (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
+    else if (use_vec)
         rc = vec_rollout<real>(ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph,
                                t1, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c,
                                g_smem_optin, st);

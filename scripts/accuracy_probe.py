@@ -13,7 +13,10 @@ from oracle import ocflow_oracle as orc
 
 torch.set_num_threads(os.cpu_count())
 print("library:", nb._cabi.LIB_PATH)
+ONLY = os.environ.get("PROBE_ONLY")
 for name, n, nt in (("softcorridor", 512, 50), ("swap2", 512, 50), ("swap12", 512, 50), ("singlequad", 512, 50), ("swarm50", 256, 80)):
+    if ONLY and name != ONLY:
+        continue
     net, prob, xinit, meta = product_setup(name, torch.float32)
     P32, D32, _, _ = oracle_setup(name, torch.float32)
     P64, D64, _, _ = oracle_setup(name, torch.float64)
