@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "noc_launch.cuh"
+#include "noc_tc_rollout.cuh"
 
 namespace noc {
 
@@ -448,12 +449,46 @@ static void stage_times_host(double t0, double t1, int nt, double* tab) {
     }
 }
 
-// the tensor-core kernel exists for fp32 only; the fp64 overload is never selected (use_tc is false) but must compile
-static int tc_launch(int d, int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n,
+// ---- tensor-core path (noc_tc_rollout.cuh): fp32, nTh = 2, m <= 128, shapes instantiated in noc_tc_inst.cu
+int launch_tc_0(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_1(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_2(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_3(const TcArgs&, int, cudaStream_t, double*);
+static int tc_shape_id(const noc_phi_t* ph, const noc_prob_t* pb) {
+    if (ph->nTh != 2 || ph->m < 1 || ph->m > 128) return -1;
+    int shape = -1;
+    if (pb->kind == NOC_PROB_QUADCOPTER && pb->nAgents == 1 && ph->d == 12) shape = 0;
+    if (pb->kind == NOC_PROB_CROSS2D && pb->agentDim == 2 && ph->d == 2 * pb->nAgents) {
+        if (pb->nAgents == 2) shape = 1;
+        if (pb->nAgents == 4) shape = 2;
+        if (pb->nAgents == 12) shape = 3;
+    }
+    if (shape < 0) return -1;
+    const int mp = align_up(ph->m, shape == 0 ? 32 : 16), KS = align_up(ph->d + 2, 16);
+    if (tc_smem_bytes(mp, KS) + 1024 > (size_t)g_smem_optin) return -1;      // e.g. d = 24 with m = 128: FMA kernels
+    return shape;
+}
+static int tc_launch(int shape, int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n,
                      const double* dt, int nt, int stepper, int mode, const double* alph, double t_end, double* sums, float* a,
                      float* b, float* c, int lim, cudaStream_t st) {
-    return tc_quad_rollout(d, m, r, h, raw, pr, x, n, dt, nt, stepper, mode, alph, t_end, sums, a, b, c, lim, st);
+    TcArgs A;
+    memset(&A, 0, sizeof A);
+    const int ch = (shape == 0) ? 32 : 16;
+    A.m = m; A.mp = align_up(m, ch); A.h = (float)h; A.r = r;
+    A.K0 = raw.K[0]; A.b0 = raw.b[0]; A.K1 = raw.K[1]; A.b1 = raw.b[1]; A.w = raw.w; A.A = raw.A; A.c_w = raw.c_w; A.c_b = raw.c_b;
+    A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.stepper = stepper; A.mode = mode; A.times = dt;
+    A.alph0 = (float)alph[0]; A.alph3 = (float)alph[3]; A.alph4 = (float)alph[4]; A.alph5 = (float)alph[5];
+    A.t_end = (float)t_end;
+    A.out_a = a; A.out_b = b; A.out_c = c;
+    switch (shape) {
+        case 0: return launch_tc_0(A, lim, st, sums);
+        case 1: return launch_tc_1(A, lim, st, sums);
+        case 2: return launch_tc_2(A, lim, st, sums);
+        case 3: return launch_tc_3(A, lim, st, sums);
+    }
+    return fail(NOC_ERR_ARG, "bad tensor-core shape %d", shape);
 }
+// the tensor-core kernel exists for fp32 only; the fp64 overload is never selected (use_tc is false) but must compile
 static int tc_launch(int, int, int, double, const PhiRaw<double>&, const ProbPack&, const double*, long long, const double*, int, int,
                      int, const double*, double, double*, double*, double*, double*, int, cudaStream_t) {
     return fail(NOC_ERR_UNSUPPORTED, "the tensor-core path is fp32 only");
@@ -493,8 +528,8 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     if (std::max(ph->m, ph->d + 4) > 1024) use_vec = false;
     // tensor-core path (noc_tc_quad.cu) for the shapes it is written for; NOC_TC=0 turns it off, NOC_FORCE_PATH=tc forces it
     bool use_tc = false;
-    if (std::is_same<real, float>::value && pb->kind == NOC_PROB_QUADCOPTER && pb->nAgents == 1 && ph->d == 12 && ph->nTh == 2 &&
-        ph->m % 16 == 0 && ph->m >= 16 && ph->m <= 128) {
+    const int tc_shape = std::is_same<real, float>::value ? tc_shape_id(ph, pb) : -1;
+    if (tc_shape >= 0) {
         const char* tc = getenv("NOC_TC");
         const char* fp = getenv("NOC_FORCE_PATH");
         use_tc = (tc && !strcmp(tc, "1") && !use_vec) || (fp && !strcmp(fp, "tc"));
@@ -521,7 +556,7 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
     A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
     if (use_tc)
-        rc = tc_launch(ph->d, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph, t1,
+        rc = tc_launch(tc_shape, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph, t1,
                        (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
     else if (use_vec)
         rc = vec_rollout<real>(ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph,

@@ -43,11 +43,6 @@ int vec_rollout(int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw,
                 const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
                 real* out_nomean, real* zFull, real* ctrlFull, int smem_limit, cudaStream_t st);
 
-// tensor-core path (noc_tc_quad.cu): fp32, one quadcopter (d = 12), nTh = 2, m % 16 == 0, m <= 128
-int tc_quad_rollout(int d, int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n,
-                    const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
-                    float* out_nomean, float* zFull, float* ctrlFull, int smem_limit, cudaStream_t st);
-
 // one translation unit per configuration (noc_inst.cu with -DNOC_CFG_ID=k) defines these
 #define NOC_DECL_LAUNCH(ID, REAL) \
     int launch_cfg_##ID(const RolloutArgs<REAL>& A, const PhiRaw<REAL>* raw, int kmode, size_t smem, cudaStream_t st, double* out_sums);

@@ -1,0 +1,23 @@
+// noc_tc_inst.cu — one translation unit per tensor-core rollout shape (compile with -DNOC_TC_SHAPE=k); see noc_tc_rollout.cuh.
+#include "noc_tc_rollout.cuh"
+
+namespace noc {
+//                              kind NA CH minb
+#if NOC_TC_SHAPE == 0
+using Shape = TcShape<2, 1, 32, 1>;     // one quadcopter, d = 12 (singlequad: m = 128, one CTA per SM)
+#elif NOC_TC_SHAPE == 1
+using Shape = TcShape<0, 2, 16, 4>;     // Cross2D, 2 agents, d = 4 (softcorridor, swap2, hardcorridor)
+#elif NOC_TC_SHAPE == 2
+using Shape = TcShape<0, 4, 16, 3>;     // Cross2D, 4 agents, d = 8 (midcross4)
+#elif NOC_TC_SHAPE == 3
+using Shape = TcShape<0, 12, 16, 2>;    // Cross2D, 12 agents, d = 24 (swap12)
+#else
+#error "NOC_TC_SHAPE must be 0..3"
+#endif
+
+#define NOC_TC_NAME2(k) launch_tc_##k
+#define NOC_TC_NAME(k) NOC_TC_NAME2(k)
+int NOC_TC_NAME(NOC_TC_SHAPE)(const TcArgs& A, int smem_limit, cudaStream_t st, double* out_sums) {
+    return launch_tc<Shape>(A, smem_limit, st, out_sums);
+}
+}  // namespace noc

@@ -1,0 +1,559 @@
+// noc_tc_rollout.cuh — tensor-core (tcgen05 / TMEM) rollout kernel, fp32 in / fp32 out, for value networks with
+// nTh = 2 and m <= 128 on problems whose state fits one thread's registers (d <= 24).
+//
+// One CTA of 128 threads owns a tile of 128 samples; THREAD r IS SAMPLE r: it keeps the augmented state z = [x, L, HJt, Q, W]
+// and the RK accumulator in registers for all nt steps, evaluates the problem terms (calcLHQW / calcGradpH / calcCtrls)
+// in registers, and is the epilogue thread of TMEM lane r.  The four contractions of one grad-Phi evaluation
+// (Phi.py:99-138) run on the 5th-generation tensor cores with M = 128 samples:
+//     GEMM-1  O  [128 x m]  = S [128 x KS] . K0b'     S = [x, t, 1, 0..]  (the 1-column folds the bias b0 in)
+//     GEMM-2  A1 [128 x m]  = U0 [128 x m] . K1'      B = K1 read K-major
+//     GEMM-3  Z1 [128 x m]  = Y  [128 x m] . K1       B = the SAME K1 buffer read MN-major
+//     GEMM-4  G  [128 x KS] = V  [128 x m] . K0b (MN-major view of the GEMM-1 buffer)  +  S . symb'  (A'A and c_w)
+// Accumulators live in TMEM (fp32); tanh(o) is parked in TMEM between GEMM-1 and GEMM-3.
+//
+// Precision: every fp32 operand is split into three bf16 terms (hi, mid, lo) and each logical product is six MMAs
+// (hh, hm, mh, hl, mm, lh; the dropped terms are O(2^-24)), because a single bf16 / tf32 pass breaks the 1e-5
+// per-step-state tolerance.  The hh products accumulate in one TMEM accumulator and the five correction
+// products in another (the tensor core truncates on every fp32 add; the small terms keep their own, 2^-8 smaller, error);
+// the epilogue adds the two in round-to-nearest fp32.  Measured on the B200: as close to the fp64 reference as the
+// fp32 FMA kernels and as torch's own fp32 (scripts/accuracy_probe.py).
+//
+// Operands are written by the epilogue threads straight into the canonical no-swizzle UMMA layout (8-row x 16-byte core
+// matrices), one thread issues the MMAs, and tcgen05.commit signals an mbarrier the 128 epilogue threads wait on.
+// Several CTAs share an SM when shared memory and TMEM columns allow, so one tile's epilogue overlaps another's MMAs.
+#pragma once
+#include "noc_launch.cuh"
+#include "noc_tc.cuh"
+
+namespace noc {
+
+struct TcArgs {
+    int m, mp;                      // hidden width and its padded value (multiple of the epilogue chunk)
+    float h;
+    const float *K0, *b0, *K1, *b1, *w, *A, *c_w, *c_b;   // reference layout (fp32, device)
+    int r;
+    ProbPack prob;
+    const float* x;
+    long long n;
+    int nt, stepper, mode;
+    const double* times;
+    float alph0, alph3, alph4, alph5, t_end;
+    double* partials;
+    float* out_a; float* out_b; float* out_c;
+    int ntiles, tmem_cols;
+};
+
+// problem shapes the kernel is instantiated for
+template <int KIND_, int NA_, int CH_, int MINB_>
+struct TcShape {
+    static constexpr int KIND = KIND_, NA = NA_;
+    static constexpr int DIM = (KIND == 2) ? 12 : (KIND == 0 ? 2 : 3);
+    static constexpr int d = NA * DIM, D = d + 1, NZ = d + 4;
+    static constexpr int KS = ((D + 1 + 15) / 16) * 16;           // K of the S operand: [x, t, 1] zero-padded
+    static constexpr int NCTRL = (KIND == 2) ? 4 * NA : d;
+    static constexpr int CH = CH_;                                 // epilogue chunk (TMEM columns per load)
+    static constexpr int MINB = MINB_;
+    static_assert(KIND != 2 || NA == 1, "one quadcopter");
+};
+
+// fp32 pair -> three packed bf16x2 terms, v ~ hi + mid + lo (exact to ~2^-24 |v|); registers only
+__device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);          // .x = a (low half), .y = b
+    return *reinterpret_cast<unsigned*>(&v);
+}
+__device__ __forceinline__ float bf_lo(unsigned p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf_hi(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
+__device__ __forceinline__ void split3x2(float a, float b, unsigned& hi, unsigned& mid, unsigned& lo) {
+    hi = pack_bf16x2(a, b);
+    const float ra = a - bf_lo(hi), rb = b - bf_hi(hi);
+    mid = pack_bf16x2(ra, rb);
+    lo = pack_bf16x2(ra - bf_lo(mid), rb - bf_hi(mid));
+}
+
+// write 8 consecutive K-elements (one 16-byte chunk) of row `row` of an A/B operand, all three split planes
+__device__ __forceinline__ void store_chunk3(unsigned char* base, int plane_bytes, int row, int k0, int K, const float* v) {
+    uint4 h, mi, l;
+    split3x2(v[0], v[1], h.x, mi.x, l.x);
+    split3x2(v[2], v[3], h.y, mi.y, l.y);
+    split3x2(v[4], v[5], h.z, mi.z, l.z);
+    split3x2(v[6], v[7], h.w, mi.w, l.w);
+    const int off = il_off(row, k0, K);
+    *reinterpret_cast<uint4*>(base + off) = h;
+    *reinterpret_cast<uint4*>(base + plane_bytes + off) = mi;
+    *reinterpret_cast<uint4*>(base + 2 * plane_bytes + off) = l;
+}
+__device__ __forceinline__ void load_chunk3(const unsigned char* base, int plane_bytes, int row, int k0, int K, float* v) {
+    const int off = il_off(row, k0, K);
+    const uint4 a = *reinterpret_cast<const uint4*>(base + off), b = *reinterpret_cast<const uint4*>(base + plane_bytes + off),
+                c = *reinterpret_cast<const uint4*>(base + 2 * plane_bytes + off);
+    const unsigned pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = (bf_lo(pa[i]) + bf_lo(pb[i])) + bf_lo(pc[i]);
+        v[2 * i + 1] = (bf_hi(pa[i]) + bf_hi(pb[i])) + bf_hi(pc[i]);
+    }
+}
+
+// one logical fp32 product block: six bf16 MMAs over the three planes of A and B (same descriptor geometry per plane);
+// hi*hi goes to `d_main`, the five correction products to `d_corr` (see the header)
+__device__ __forceinline__ void mma6(unsigned d_main, unsigned d_corr, unsigned a_addr, int a_plane, unsigned a_lbo, unsigned a_sbo,
+                                     unsigned b_addr, int b_plane, unsigned b_lbo, unsigned b_sbo, unsigned idesc, int accumulate) {
+    umma_bf16(d_main, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accumulate);                       // hh
+    umma_bf16(d_corr, umma_desc(a_addr + 2 * a_plane, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accumulate);         // lh
+    umma_bf16(d_corr, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr + 2 * b_plane, b_lbo, b_sbo), idesc, 1);                  // hl
+    umma_bf16(d_corr, umma_desc(a_addr + a_plane, a_lbo, a_sbo), umma_desc(b_addr + b_plane, b_lbo, b_sbo), idesc, 1);            // mm
+    umma_bf16(d_corr, umma_desc(a_addr + a_plane, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, 1);                      // mh
+    umma_bf16(d_corr, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr + b_plane, b_lbo, b_sbo), idesc, 1);                      // hm
+}
+
+// v[0..CH) = [ta] + [tb]: two accumulators summed in round-to-nearest fp32, one wait for both loads
+template <int CH>
+__device__ __forceinline__ void tmem_ld_sum(unsigned ta, unsigned tb, float* v) {
+    unsigned r[CH], q[CH];
+    if constexpr (CH == 32) { tmem_ld32_issue(ta, r); tmem_ld32_issue(tb, q); }
+    else { tmem_ld16_issue(ta, r); tmem_ld16_issue(tb, q); }
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
+}
+template <int CH>
+__device__ __forceinline__ void tmem_ld(unsigned ta, float* v) {
+    unsigned r[CH];
+    if constexpr (CH == 32) tmem_ld32_issue(ta, r); else tmem_ld16_issue(ta, r);
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+}
+template <int CH>
+__device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
+    unsigned r[CH];
+#pragma unroll
+    for (int i = 0; i < CH; ++i) r[i] = __float_as_uint(v[i]);
+    if constexpr (CH == 32) tmem_st32_bits(ta, r); else tmem_st16_bits(ta, r);
+}
+
+// bytes of dynamic shared memory for (mp, KS)
+static inline size_t tc_smem_bytes(int mp, int KS) {
+    return 3 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
+           sizeof(float) * (2 * (size_t)mp + KS + 32);
+}
+static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) | terminal-only S.symb corr
+    int need = 3 * std::max(mp, KS) + KS, c = 32;
+    while (c < need) c *= 2;
+    return c;
+}
+
+template <class SH>
+__global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs A) {
+    constexpr int d = SH::d, D = SH::D, KS = SH::KS, NZ = SH::NZ, NCTRL = SH::NCTRL, CH = SH::CH, KIND = SH::KIND;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int m = A.m, mp = A.mp;
+    const ProbPack& pr = A.prob;
+    // shared-memory map (bytes); every operand has three planes (hi, mid, lo)
+    const int pK1 = mp * mp * 2, pK0 = mp * KS * 2, pX = 128 * mp * 2;
+    constexpr int pSy = KS * KS * 2, pS = 128 * KS * 2;
+    unsigned char* sK1 = smem;
+    unsigned char* sK0 = sK1 + 3 * pK1;
+    unsigned char* sSy = sK0 + 3 * pK0;
+    unsigned char* sX = sSy + 3 * pSy;
+    unsigned char* sS = sX + 3 * pX;
+    float* sb1 = reinterpret_cast<float*>(sS + 3 * pS);
+    float* sw = sb1 + mp;
+    float* scw = sw + mp;                                // KS floats
+    float* sred = scw + KS;                              // 4 warps x 8
+    __shared__ __align__(8) unsigned long long mbar;
+    __shared__ unsigned tmem_base_s;
+
+    // ---- one-time per CTA: weights -> split bf16 operands in canonical layout (padded units have zero weights: they
+    //      contribute exactly nothing to any contraction)
+    for (int i = tid; i < mp * (mp / 8); i += 128) {     // K1[o][k0..k0+8)
+        const int o = i / (mp / 8), k0 = (i % (mp / 8)) * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = (o < m && k0 + e < m) ? A.K1[o * m + k0 + e] : 0.f;
+        store_chunk3(sK1, pK1, o, k0, mp, v);
+    }
+    for (int i = tid; i < mp * (KS / 8); i += 128) {     // K0b[j][k]: K0 | b0 | 0
+        const int j = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { const int k = k0 + e; v[e] = (j >= m) ? 0.f : ((k < D) ? A.K0[j * D + k] : (k == D ? A.b0[j] : 0.f)); }
+        store_chunk3(sK0, pK0, j, k0, KS, v);
+    }
+    for (int i = tid; i < KS * (KS / 8); i += 128) {     // symb[n = k'][k]: (A'A)[k][k'] | c_w[k'] in column D | 0
+        const int kp = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
+        float v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int k = k0 + e;
+            float s = 0.f;
+            if (kp < D && k < D) { for (int q = 0; q < A.r; ++q) s = fmaf(A.A[q * D + k], A.A[q * D + kp], s); }
+            else if (kp < D && k == D) s = A.c_w[kp];
+            v[e] = s;
+        }
+        store_chunk3(sSy, pSy, kp, k0, KS, v);
+    }
+    for (int i = tid; i < mp; i += 128) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] : 0.f; }
+    if (tid < KS) scw[tid] = (tid < D) ? A.c_w[tid] : 0.f;
+    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), A.tmem_cols);
+    if (tid == 0) mbar_init(smem_u32(&mbar), 1);
+    fence_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const int C = (mp > KS) ? mp : KS;
+    const unsigned tacc = tmem_base_s;                   // hi*hi accumulator, columns [0, C)
+    const unsigned tcor = tacc + C;                      // correction-term accumulator, same column map
+    const unsigned tT0 = tacc + 2 * C;                   // tanh(o); at the terminal evaluation also S.symb' (main)
+    const unsigned tTq = tacc + 3 * C;                   // terminal evaluation only: S.symb' (corrections), KS columns
+    const unsigned lane_bits = (unsigned)(warp * 32) << 16;
+    const unsigned mb = smem_u32(&mbar);
+    int phase = 0;
+    const unsigned idesc_m_k = umma_idesc_bf16(128, mp, 0), idesc_m_mn = umma_idesc_bf16(128, mp, 1);
+    const unsigned idesc_s_mn = umma_idesc_bf16(128, KS, 1), idesc_s_k = umma_idesc_bf16(128, KS, 0);
+    const unsigned aX = smem_u32(sX), aS = smem_u32(sS), aK1 = smem_u32(sK1), aK0 = smem_u32(sK0), aSy = smem_u32(sSy);
+    const unsigned sboM = (unsigned)(mp >> 3) * 128;     // 8-row-group stride of an operand with K = mp
+    constexpr unsigned sboS = (unsigned)(KS >> 3) * 128; // ... with K = KS
+
+    // publish my operand writes, let thread 0 issue `issue`, wait for the tensor core
+    auto run_mma = [&](auto issue) {
+        fence_async_smem();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            issue();
+            umma_commit(mb);
+        }
+        mbar_wait(mb, phase);
+        phase ^= 1;
+        tc_fence_after();
+    };
+
+    // grad Phi at s = [xs, t] -> g[0..D); terminal: also Phi(s)
+    auto chain = [&](const float (&xs)[d], float t, float (&g)[KS], bool terminal, float& phi_out) {
+#pragma unroll
+        for (int c0 = 0; c0 < KS; c0 += 8) {             // S operand row: [x, t, 1, 0..]
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = (k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f)); }
+            store_chunk3(sS, pS, tid, c0, KS, v);
+        }
+        run_mma([&] {                                    // GEMM-1: O = S . K0b'
+#pragma unroll
+            for (int kb = 0; kb < KS / 16; ++kb)
+                mma6(tacc, tcor, aS + kb * 256, pS, 128, sboS, aK0 + kb * 256, pK0, 128, sboS, idesc_m_k, kb > 0);
+        });
+        for (int c0 = 0; c0 < mp; c0 += CH) {            // u0 = act(o) -> X operand, tanh(o) -> TMEM
+            float v[CH], tt[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) act_tanh(v[i], v[i], tt[i]);
+            tmem_st<CH>(tT0 + lane_bits + c0, tt);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
+        }
+        run_mma([&] {                                    // GEMM-2: A1 = U0 . K1'  (B K-major)
+            for (int kb = 0; kb < mp / 16; ++kb)
+                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK1 + kb * 256, pK1, 128, sboM, idesc_m_k, kb > 0);
+        });
+        float phiN = 0.f;
+        for (int c0 = 0; c0 < mp; c0 += CH) {            // y = tanh(a1 + b1) * w -> X operand
+            float v[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) {
+                float u8[8];
+                if (terminal) load_chunk3(sX, pX, tid, c0 + q * 8, mp, u8);      // u0, before it is overwritten
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int col = c0 + q * 8 + e;
+                    const float pre = v[q * 8 + e] + sb1[col], wv = sw[col];
+                    if (terminal) {
+                        float av, tv;
+                        act_tanh(pre, av, tv);
+                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);
+                        v[q * 8 + e] = tv * wv;
+                    } else {
+                        v[q * 8 + e] = tanh_only(pre) * wv;
+                    }
+                }
+                store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
+            }
+        }
+        run_mma([&] {                                    // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
+            for (int kb = 0; kb < mp / 16; ++kb)
+                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK1 + kb * 2 * sboM, pK1, sboM, 128, idesc_m_mn, kb > 0);
+        });
+        for (int c0 = 0; c0 < mp; c0 += CH) {            // v = tanh(o) * (w + h z1acc) -> X operand
+            float v[CH], tt[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+            tmem_ld<CH>(tT0 + lane_bits + c0, tt);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = tt[i] * (sw[c0 + i] + A.h * v[i]);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
+        }
+        run_mma([&] {                                    // GEMM-4: G = V . K0b (MN-major view) + S . symb'
+            for (int kb = 0; kb < mp / 16; ++kb)
+                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK0 + kb * 2 * sboS, pK0, sboS, 128, idesc_s_mn, kb > 0);
+            // the terminal evaluation needs S.symb' on its own (Phi's quadratic term): it goes to the free tanh columns
+            const unsigned qm = terminal ? tT0 : tacc, qc = terminal ? tTq : tcor;
+#pragma unroll
+            for (int kb = 0; kb < KS / 16; ++kb)
+                mma6(qm, qc, aS + kb * 256, pS, 128, sboS, aSy + kb * 256, pSy, 128, sboS, idesc_s_k, terminal ? (kb > 0) : 1);
+        });
+#pragma unroll
+        for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tacc + lane_bits + c0, tcor + lane_bits + c0, g + c0);
+        if (terminal) {                                   // Phi = w.u1 + 0.5 s'A'A s + c_w.s + c_b  (Phi.py:96)
+            float gq[KS];
+#pragma unroll
+            for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tT0 + lane_bits + c0, tTq + lane_bits + c0, gq + c0);
+            float quad = 0.f, lin = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float sv = (k < d) ? xs[k < d ? k : 0] : t;
+                quad = fmaf(sv, gq[k] - scw[k], quad);   // gq carries c_w (column D of symb)
+                lin = fmaf(scw[k], sv, lin);
+                g[k] += gq[k];
+            }
+            phi_out = phiN + 0.5f * quad + (lin + A.c_b[0]);
+        }
+    };
+
+    // calcLHQW / calcGradpH / calcCtrls in registers: dx = -grad_p H, cost rates L, HJ = |Phi_t - H|, Q, W; uctrl = the
+    // quadcopter thrust (Cross2D.py:69-87,133-165; Quadcopter.py:65-113,160-197)
+    auto problem = [&](const float (&x)[d], const float (&g)[KS], float (&dx)[d], float (&rate)[4], float& uctrl) {
+        if constexpr (KIND == 2) {
+            float sps, cps, sth, cth, sph, cph;
+            sincosf(x[3], &sps, &cps); sincosf(x[4], &sth, &cth); sincosf(x[5], &sph, &cph);
+            const float f7 = sps * sph + cps * sth * cph, f8 = -cps * sph + sps * sth * cph, f9 = cth * cph;
+            const float fp = f7 * g[6] + f8 * g[7] + f9 * g[8];
+            const float u = float(-1.0 / (2.0 * pr.mass)) * fp;
+            const float sq = g[9] * g[9] + g[10] * g[10] + g[11] * g[11];
+            float L = float(pr.alph_Q) * 0.f;
+            L = L + 2.f + u * u + 0.25f * sq;
+            const float um = u / float(pr.mass);
+            const float xv = x[6] * g[0] + x[7] * g[1] + x[8] * g[2];
+            const float xw = x[9] * g[3] + x[10] * g[4] + x[11] * g[5];
+            const float H = 0.f - L - xv - xw - um * fp + float(pr.grav) * g[8] + 0.5f * sq;
+            rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = 0.f; rate[3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dx[c] = x[6 + c];
+            dx[6] = -(-um * f7); dx[7] = -(-um * f8); dx[8] = -(-um * f9 + float(pr.grav));
+#pragma unroll
+            for (int c = 9; c < 12; ++c) dx[c] = -(0.5f * g[c]);
+            uctrl = u;
+        } else {
+            constexpr int NA = SH::NA, DIM = SH::DIM;
+            float pp = 0.f, q = 0.f, w = 0.f;
+#pragma unroll
+            for (int r = 0; r < d; ++r) pp = fmaf(g[r], g[r], pp);
+            if ((pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0)) {
+#pragma unroll
+                for (int a = 0; a < NA; ++a) q += terrain_agent<float>(pr, x[a * DIM], x[a * DIM + 1], DIM == 3 ? x[a * DIM + DIM - 1] : 0.f);
+            }
+            if (pr.alph_W != 0.0 && NA >= 2) {
+                const float cut = float(pr.cutW), c2 = float(2 * pr.r * pr.r);
+                if constexpr (NA == 2) {               // Cross2D.py:133-145: no "== 1" rule here
+                    float d2 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < DIM; ++c) { const float df = x[c] - x[DIM + c]; d2 = fmaf(df, df, d2); }
+                    const float dd = sqrtf(d2);
+                    if (dd < cut) w = r_exp(-(dd * dd) / c2);
+                } else {                               // Cross2D.py:147-160; same fast path as interaction_pairs()
+                    const float guard = cut * cut * 1.0001f;
+                    float dmin = guard;
+#pragma unroll
+                    for (int i = 0; i < NA - 1; ++i)
+#pragma unroll
+                        for (int j = i + 1; j < NA; ++j) {
+                            float d2 = 0.f;
+#pragma unroll
+                            for (int c = 0; c < DIM; ++c) { const float df = x[i * DIM + c] - x[j * DIM + c]; d2 = fmaf(df, df, d2); }
+                            dmin = fminf(dmin, d2);
+                        }
+                    if (dmin < guard) {                // rare: redo the pairs exactly, in the same order
+#pragma unroll
+                        for (int i = 0; i < NA - 1; ++i)
+#pragma unroll
+                            for (int j = i + 1; j < NA; ++j) {
+                                float d2 = 0.f;
+#pragma unroll
+                                for (int c = 0; c < DIM; ++c) { const float df = x[i * DIM + c] - x[j * DIM + c]; d2 = fmaf(df, df, d2); }
+                                if (d2 < guard) {
+                                    const float dd = sqrtf(d2);
+                                    if (dd < cut) {
+                                        const float e = r_exp(-(dd * dd) / c2);
+                                        if (e != 1.f) w += e;      // pairs whose Gaussian rounds to 1 are dropped (mask2)
+                                    }
+                                }
+                            }
+                    }
+                }
+            }
+            float Qret, L;
+            if (pr.kind == 0) { Qret = float(pr.alph_Q) * q; L = 0.5f * pp + Qret; }     // Cross2D returns Q pre-scaled (quirk 6)
+            else { Qret = (pr.alph_Q > 0.0) ? q : 0.f; L = 0.5f * pp + float(pr.alph_Q) * Qret; }
+            if (pr.alph_W != 0.0) L = L + float(pr.alph_W) * w; else w = 0.f;
+            const float H = -L + pp;
+            rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = Qret; rate[3] = w;
+#pragma unroll
+            for (int c = 0; c < d; ++c) dx[c] = -g[c];
+            uctrl = 0.f;
+        }
+    };
+
+    double csum[7] = {0, 0, 0, 0, 0, 0, 0};
+    long long cnt = 0;
+    const int nstage = (A.stepper == 4) ? 4 : (A.stepper == 1 ? 1 : 0);
+    const bool inter = (A.mode == 2);
+    const int ntp1 = A.nt + 1;
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const long long s0 = (long long)tile * 128;
+        const int nvalid = (int)((A.n - s0 < 128) ? (A.n - s0) : 128);
+        const bool valid = tid < nvalid;
+        const long long gs = s0 + (valid ? tid : nvalid - 1);        // padding threads replay the last valid sample
+        float z0[NZ], za[NZ];
+#pragma unroll
+        for (int c = 0; c < d; ++c) z0[c] = A.x[gs * d + c];
+#pragma unroll
+        for (int c = d; c < NZ; ++c) z0[c] = 0.f;
+        if (inter && valid) {                                          // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
+#pragma unroll
+            for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1] = z0[c];
+#pragma unroll
+            for (int c = 0; c < NCTRL; ++c) A.out_c[(gs * NCTRL + c) * ntp1] = 0.f;
+        }
+        // ONE call site for the chain: the nt * (stages [+ 1 control evaluation]) + 1 terminal evaluations of a tile are a
+        // flat sequence; `xs` always holds the next evaluation's input.
+        float g[KS], dx[d], xs[d], phi1 = 0.f;
+#pragma unroll
+        for (int c = 0; c < d; ++c) xs[c] = z0[c];
+        const int per = nstage + (inter ? 1 : 0);
+        const int total = A.nt * per + 1;
+        for (int it = 0; it < total; ++it) {
+            const bool term = (it == total - 1);
+            const int k = term ? 0 : it / per, st = term ? 0 : it % per;
+            const bool ctl = !term && st == nstage;                 // control evaluation after the step (OCflow.py:51-55)
+            const double* tt = A.times + 5 * k;
+            const float hstep = float(tt[4]);                       // h = t1 - t0 recomputed per step (OCflow.py:169)
+            float wgt = 1.f, cnext = 0.f, tcur = float(tt[0]);
+            if (term) tcur = A.t_end;
+            else if (ctl) tcur = float(tt[3]);                      // new state, OLD time (quirk 3)
+            else if (nstage == 4) {                                 // RK4 weights (OCflow.py:172-182)
+                if (st == 0) { wgt = float(1.0 / 6.0); cnext = 0.5f; }
+                else if (st == 1) { wgt = float(2.0 / 6.0); cnext = 0.5f; tcur = float(tt[1]); }
+                else if (st == 2) { wgt = float(2.0 / 6.0); cnext = 1.0f; tcur = float(tt[1]); }
+                else { wgt = float(1.0 / 6.0); tcur = float(tt[2]); }
+            }
+            chain(xs, tcur, g, term, phi1);
+            if (term) break;
+            float rate[4], uc;
+            problem(xs, g, dx, rate, uc);
+            if (ctl) {
+                if (valid) {
+#pragma unroll
+                    for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1 + (k + 1)] = z0[c];
+                    if constexpr (KIND == 2) {
+                        A.out_c[(gs * 4 + 0) * ntp1 + (k + 1)] = uc;
+#pragma unroll
+                        for (int c = 1; c < 4; ++c) A.out_c[(gs * 4 + c) * ntp1 + (k + 1)] = -0.5f * g[8 + c];
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < d; ++c) A.out_c[(gs * d + c) * ntp1 + (k + 1)] = -g[c];
+                    }
+                }
+                continue;
+            }
+#pragma unroll
+            for (int c = 0; c < NZ; ++c) {
+                float kk;
+                if (c < d) kk = (KIND == 2) ? hstep * dx[c < d ? c : 0] : hstep * (-g[c]);
+                else kk = hstep * rate[c >= d ? c - d : 0];
+                za[c] = ((st == 0) ? z0[c] : za[c]) + wgt * kk;
+                if (c < d) dx[c < d ? c : 0] = kk;
+            }
+            if (st != nstage - 1) {
+#pragma unroll
+                for (int c = 0; c < d; ++c) xs[c] = z0[c] + cnext * dx[c];
+            } else {
+#pragma unroll
+                for (int c = 0; c < NZ; ++c) z0[c] = za[c];
+#pragma unroll
+                for (int c = 0; c < d; ++c) xs[c] = z0[c];
+            }
+        }
+        // terminal block (OCflow.py:58-90): xs = x(T), g = grad Phi(x(T), T), phi1 = Phi(x(T), T)
+        const float* xt = static_cast<const float*>(pr.xtarget);
+        float cG = 0.f, hjg = 0.f;
+#pragma unroll
+        for (int c = 0; c < d; ++c) {
+            const float res = xs[c] - xt[c];
+            cG = fmaf(res, res, cG);
+            hjg += fabsf(g[c] - A.alph0 * res);
+        }
+        cG *= 0.5f;
+        const float cost[7] = {z0[d], cG, z0[d + 1], fabsf(phi1 - A.alph0 * cG), hjg, z0[d + 2], z0[d + 3]};
+        if (A.mode == 0) {
+            // deterministic CTA sum: lanes -> warp (shuffle tree), warps -> thread 0 in fixed order
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                float v = valid ? cost[q] : 0.f;
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+                if ((tid & 31) == 0) sred[warp * 8 + q] = v;
+            }
+            __syncthreads();
+            if (tid == 0) {
+                for (int q = 0; q < 7; ++q) csum[q] += (double)sred[q] + (double)sred[8 + q] + (double)sred[16 + q] + (double)sred[24 + q];
+                cnt += nvalid;
+            }
+            __syncthreads();
+        } else if (A.mode == 1 && valid) {
+            float* o = A.out_a + gs * 8;
+            o[0] = cost[0] + A.alph0 * cost[1] + A.alph3 * cost[2] + A.alph4 * cost[3] + A.alph5 * cost[4];   // OCflow.py:75
+#pragma unroll
+            for (int q = 0; q < 7; ++q) o[1 + q] = cost[q];
+        }
+    }
+    if (A.mode == 0 && A.partials && tid == 0) {
+        for (int q = 0; q < 7; ++q) A.partials[blockIdx.x * 8 + q] = csum[q];
+        A.partials[blockIdx.x * 8 + 7] = (double)cnt;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tacc, A.tmem_cols);
+}
+
+template <class SH>
+int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
+    const size_t smem = tc_smem_bytes(A.mp, SH::KS);
+    auto kern = rollout_tc_kernel<SH>;
+    if (smem + 1024 > (size_t)smem_limit) return fail(NOC_ERR_NOMEM, "tensor-core rollout needs %zu B of shared memory", smem);
+    NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    A.tmem_cols = tc_tmem_cols(A.mp, SH::KS);
+    per_sm = std::min(per_sm, 512 / A.tmem_cols);       // a CTA that cannot get its TMEM columns would only wait
+    if (per_sm < 1) return fail(NOC_ERR_NOMEM, "tensor-core rollout does not fit on an SM");
+    A.ntiles = (int)((A.n + 127) / 128);
+    const int grid = std::max(1, std::min(A.ntiles, per_sm * sm_count()));
+    double* partials = nullptr;
+    if (A.mode == NOC_MODE_MEAN) {
+        NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)grid, st));
+        A.partials = partials;
+    }
+    kern<<<grid, 128, smem, st>>>(A);
+    count_launch();
+    NOC_CUDA(cudaGetLastError());
+    if (partials) {
+        int frc = launch_finish(partials, grid, out_sums, st);
+        if (frc) return frc;
+        NOC_CUDA(cudaFreeAsync(partials, st));
+    }
+    return NOC_OK;
+}
+
+}  // namespace noc

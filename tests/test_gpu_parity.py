@@ -41,8 +41,10 @@ def _three_modes(nb, x, net, prob, tspan, nt, stepper, alph):
     return mean, nomean, zf.cpu().numpy(), cf.cpu().numpy()
 
 
-def _compare(tag, d, got, ref, what):
-    tol = TOL[tag]
+def _compare(tag, d, got, ref, what, state_tol=None):
+    tol = dict(TOL[tag])
+    if state_tol is not None:
+        tol["state"] = state_tol
     mean, nomean, zf, cf = got
     rmean, rnomean, rz, rc = ref
     assert zf.shape == rz.shape and cf.shape == rc.shape, what
