@@ -49,6 +49,41 @@ DRAM_BYTES_PER_SAMPLE = {"swap12": (12.838656e6 + 1.28e6) / 131072, "swarm50": (
                          "singlequad": (6.871808e6 + 294.912e6) / 131072}
 
 
+def tensor_flops_per_sample_step(d, m):
+    """bf16 tensor-core flops the tcgen05 kernel EXECUTES per sample-step (noc_tc_rollout.cuh): 4 evaluations x 6 split
+    products x 2 flops x the padded GEMM volumes  KS*mp + 2*mp*mp + mp*KS + KS*KS."""
+    ks = -(-(d + 2) // 16) * 16
+    mp = -(-m // (64 if d == 12 else 16)) * (64 if d == 12 else 16)
+    return 4 * 6 * 2 * (ks * mp + 2 * mp * mp + mp * ks + ks * ks)
+
+
+def roofline(workload, W, d, meta, n, nt, fl, step_s, fma_peak, path):
+    """Roofline of the rollout kernel of one launch.  FMA kernels: algorithmic fp32/fp64 flops against the FMA peak measured
+    live.  Tensor-core kernel: the bf16 flops it executes against MEASURED_PEAKS.json's sustained dense bf16 figure; the
+    algorithmic (fp32-equivalent) rate and the FMA peak stay alongside, since that ratio is what the kernel replaces."""
+    alg = n * nt * fl / step_s / 1e12
+    traffic = DRAM_BYTES_PER_SAMPLE[workload] * n if workload in DRAM_BYTES_PER_SAMPLE else None
+    note = ("DRAM bytes per launch = measured bytes per sample of the ncu capture in profiles/ x samples; "
+            "algorithmic = %d bytes (4 d per sample)" % (4 * d * n))
+    if path == "tensor":
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        tpeak = float(peaks.get("bf16_tflops_sustained", 0) or 0) or 2250.0
+        src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks.get("bf16_tflops_sustained")
+               else "B200_PROFILING.md fallback: nominal dense bf16 2250 TFLOP/s")
+        ach = n * nt * tensor_flops_per_sample_step(d, meta["m"]) / step_s / 1e12
+        return {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic,
+                "traffic_note": note, "peak_source": src, "kernel": "rollout_tc_kernel (tcgen05, 3-way bf16 split: 6 MMAs per fp32 product)",
+                "algorithmic_fp32_tflops": alg, "fp32_fma_peak_tflops": fma_peak, "algorithmic_over_fma_peak": alg / fma_peak}
+    return {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "achieved": alg, "peak": fma_peak, "unit": "TFLOP/s",
+            "frac": alg / fma_peak, "traffic": traffic, "traffic_note": note, "kernel": "rollout_kernel (FMA sample tiles)",
+            "peak_source": "measured live: register-resident FMA micro-benchmark on all SMs (noc_measure_fma_peak); "
+                           "MEASURED_PEAKS.json has no FP32/FP64 FMA figure"}
+
+
 def flops_per_sample_step(d, m, nTh, r):
     D = d + 1
     return 4 * (4 * m * D + 4 * m * m * (nTh - 1) + min(2 * D * D, 4 * r * D))
@@ -350,6 +385,7 @@ def main():
     tot_s = float(tot_ms) * 1e-3
     value = world * n * nt * args.steps / tot_s
     Jc, cs = nb.costs_from_sums(sums, alph, dtype)
+    path = nb._cabi.last_path()
 
     # ---- e2e: public API with HOST buffers (H2D of the step's inputs + D2H of its result inside the timed region)
     xh = x.cpu().pin_memory()
@@ -391,13 +427,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "sample-steps/s", "h2d_bytes_per_step": int(xh.numel() * xh.element_size()),
                     "d2h_bytes_per_step": 64},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "achieved": ach, "peak": peak,
-                         "unit": "TFLOP/s", "frac": ach / peak,
-                         "traffic": (DRAM_BYTES_PER_SAMPLE[args.workload] * n if args.workload in DRAM_BYTES_PER_SAMPLE else None),
-                         "traffic_note": "DRAM bytes per launch = measured bytes per sample of the ncu capture in profiles/ x samples; "
-                                         "algorithmic = %d bytes (4 d per sample)" % (4 * d * n),
-                         "peak_source": "measured live: register-resident FMA micro-benchmark on all SMs (noc_measure_fma_peak); "
-                                        "MEASURED_PEAKS.json has no FP32/FP64 FMA figure"},
+            "roofline": roofline(args.workload, W, d, meta, n, nt, fl, statistics.mean(step_ms) * 1e-3, peak, path),
         }
         if world == 1 and not args.no_cpu_baseline:
             lat = latency_mode(args, W, dtype, threads)     # the other half of BASELINE.json's metric

@@ -145,9 +145,15 @@ int noc_measure_fma_peak(int32_t dtype, double* tflops);
 /* Self-test of the Blackwell tensor-core building blocks (tcgen05.mma with TMEM accumulators, no-swizzle shared-memory
  * descriptors in both majors, tcgen05.ld/st, tcgen05.commit -> mbarrier): one CTA computes D[128,N] = A[128,K] * B in bf16
  * with fp32 accumulation.  B is [N,K] (b_mn_major = 0) or [K,N] read MN-major (b_mn_major = 1).  All pointers dev.
- * Diagnostics for the tensor-core rollout path under construction; not used by noc_ocflow. */
+ * Diagnostics for the building blocks of the tensor-core rollout kernel; not used by noc_ocflow. */
 int noc_tc_probe(const void* A_bf16, const void* B_bf16, void* D_f32, int32_t N, int32_t K, int32_t b_mn_major,
                  int32_t roundtrip_tmem, void* stream);
+
+/* Which kernel family the calling thread's last noc_ocflow / noc_ocflow_host call ran (-1 before the first call):
+ * the FMA sample-tile kernel, the one-CTA-per-sample small-batch kernel, or the tensor-core kernel.  The choice is made
+ * from the shapes and the batch size; env NOC_TC=0 disables the tensor-core kernel, NOC_FORCE_PATH=tile|vec|tc pins one. */
+enum { NOC_PATH_TILE = 0, NOC_PATH_SAMPLE = 1, NOC_PATH_TENSOR = 2 };
+int noc_last_path(void);
 
 /* Kernel-launch counter (number of CUDA kernels this library launched in this process); bench.py reports it. */
 int64_t noc_launch_count(void);

@@ -19,7 +19,8 @@ MODE_MEAN, MODE_NOMEAN, MODE_INTERMEDIATES = 0, 1, 2
 
 # every symbol include/noc_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ["noc_version", "noc_last_error", "noc_device_info", "noc_ctrl_dim", "noc_stage_times", "noc_ocflow",
-           "noc_ocflow_host", "noc_phi_eval", "noc_prob_eval", "noc_measure_fma_peak", "noc_tc_probe", "noc_launch_count"]
+           "noc_ocflow_host", "noc_phi_eval", "noc_prob_eval", "noc_measure_fma_peak", "noc_tc_probe", "noc_launch_count",
+           "noc_last_path"]
 
 
 class PhiT(C.Structure):
@@ -77,6 +78,14 @@ def lib():
 def check(rc):
     if rc != 0:
         raise NocError("noc error %d: %s" % (rc, lib().noc_last_error().decode("utf-8", "replace")))
+
+
+PATH_NAMES = {-1: "none", 0: "tile", 1: "sample", 2: "tensor"}
+
+
+def last_path():
+    """Kernel family of this thread's last rollout: 'tile' (FMA), 'sample' (small batch) or 'tensor' (tcgen05)."""
+    return PATH_NAMES[int(lib().noc_last_path())]
 
 
 def launch_count():

@@ -22,6 +22,7 @@ namespace noc {
 
 static thread_local std::string g_err;
 static std::atomic<long long> g_launches{0};
+static thread_local int g_last_path = -1;      // NOC_PATH_* of the calling thread's last rollout
 
 int fail(int code, const char* fmt, ...) {
     char buf[1024];
@@ -464,29 +465,39 @@ static int tc_shape_id(const noc_phi_t* ph, const noc_prob_t* pb) {
         if (pb->nAgents == 12) shape = 3;
     }
     if (shape < 0) return -1;
-    const int mp = align_up(ph->m, shape == 0 ? 32 : 16), KS = align_up(ph->d + 2, 16);
+    const int mp = align_up(ph->m, shape == 0 ? 64 : 16), KS = align_up(ph->d + 2, 16);
     if (tc_smem_bytes(mp, KS) + 1024 > (size_t)g_smem_optin) return -1;      // e.g. d = 24 with m = 128: FMA kernels
     return shape;
 }
 static int tc_launch(int shape, int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n,
-                     const double* dt, int nt, int stepper, int mode, const double* alph, double t_end, double* sums, float* a,
+                     const double* host_times, int nt, int stepper, int mode, const double* alph, double t_end, double* sums, float* a,
                      float* b, float* c, int lim, cudaStream_t st) {
     TcArgs A;
     memset(&A, 0, sizeof A);
-    const int ch = (shape == 0) ? 32 : 16;
+    const int ch = (shape == 0) ? 64 : 16;               // epilogue chunk x threads per sample of the shape (noc_tc_inst.cu)
     A.m = m; A.mp = align_up(m, ch); A.h = (float)h; A.r = r;
     A.K0 = raw.K[0]; A.b0 = raw.b[0]; A.K1 = raw.K[1]; A.b1 = raw.b[1]; A.w = raw.w; A.A = raw.A; A.c_w = raw.c_w; A.c_b = raw.c_b;
-    A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.stepper = stepper; A.mode = mode; A.times = dt;
+    A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.stepper = stepper; A.mode = mode;
     A.alph0 = (float)alph[0]; A.alph3 = (float)alph[3]; A.alph4 = (float)alph[4]; A.alph5 = (float)alph[5];
     A.t_end = (float)t_end;
     A.out_a = a; A.out_b = b; A.out_c = c;
+    std::vector<TcEval> ev;
+    tc_build_evals(host_times, nt, stepper, mode == NOC_MODE_INTERMEDIATES, t_end, ev);
+    TcEval* dev = nullptr;
+    NOC_CUDA(cudaMallocAsync((void**)&dev, sizeof(TcEval) * ev.size(), st));
+    NOC_CUDA(cudaMemcpyAsync(dev, ev.data(), sizeof(TcEval) * ev.size(), cudaMemcpyHostToDevice, st));   // pageable: staged before return
+    A.evals = dev; A.nevals = (int)ev.size();
+    int rc;
     switch (shape) {
-        case 0: return launch_tc_0(A, lim, st, sums);
-        case 1: return launch_tc_1(A, lim, st, sums);
-        case 2: return launch_tc_2(A, lim, st, sums);
-        case 3: return launch_tc_3(A, lim, st, sums);
+        case 0: rc = launch_tc_0(A, lim, st, sums); break;
+        case 1: rc = launch_tc_1(A, lim, st, sums); break;
+        case 2: rc = launch_tc_2(A, lim, st, sums); break;
+        case 3: rc = launch_tc_3(A, lim, st, sums); break;
+        default: rc = fail(NOC_ERR_ARG, "bad tensor-core shape %d", shape);
     }
-    return fail(NOC_ERR_ARG, "bad tensor-core shape %d", shape);
+    cudaError_t e = cudaFreeAsync(dev, st);
+    if (rc == NOC_OK && e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));
+    return rc;
 }
 // the tensor-core kernel exists for fp32 only; the fp64 overload is never selected (use_tc is false) but must compile
 static int tc_launch(int, int, int, double, const PhiRaw<double>&, const ProbPack&, const double*, long long, const double*, int, int,
@@ -529,12 +540,15 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     // tensor-core path (noc_tc_quad.cu) for the shapes it is written for; NOC_TC=0 turns it off, NOC_FORCE_PATH=tc forces it
     bool use_tc = false;
     const int tc_shape = std::is_same<real, float>::value ? tc_shape_id(ph, pb) : -1;
-    if (tc_shape >= 0) {
+    if (tc_shape >= 0) {                                  // on by default; NOC_TC=0 keeps the FMA kernels
         const char* tc = getenv("NOC_TC");
         const char* fp = getenv("NOC_FORCE_PATH");
-        use_tc = (tc && !strcmp(tc, "1") && !use_vec) || (fp && !strcmp(fp, "tc"));
+        use_tc = !use_vec && !(tc && !strcmp(tc, "0"));
+        if (fp && !strcmp(fp, "tc")) use_tc = true;
+        if (fp && (!strcmp(fp, "tile") || !strcmp(fp, "vec"))) use_tc = false;
         if (use_tc) use_vec = false;
     }
+    g_last_path = use_tc ? NOC_PATH_TENSOR : (use_vec ? NOC_PATH_SAMPLE : NOC_PATH_TILE);
 
     int cfg_id = -1;
     size_t smem = 0;
@@ -556,7 +570,7 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
     A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
     if (use_tc)
-        rc = tc_launch(tc_shape, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph, t1,
+        rc = tc_launch(tc_shape, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, tab.data(), nt, stepper, mode, alph, t1,
                        (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
     else if (use_vec)
         rc = vec_rollout<real>(ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph,
@@ -654,6 +668,7 @@ extern "C" {
 int noc_version(void) { return NOC_ABI_VERSION; }
 const char* noc_last_error(void) { return g_err.c_str(); }
 int64_t noc_launch_count(void) { return (int64_t)g_launches.load(); }
+int noc_last_path(void) { return g_last_path; }
 
 int noc_device_info(int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* smem_optin_bytes) {
     int rc = device_facts();

@@ -30,6 +30,13 @@ __device__ __forceinline__ void umma_bf16(unsigned d_tmem, unsigned long long a_
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
                  :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
 }
+// one lane of a converged warp (the pattern the compiler recognises as "single thread": no per-lane replay of the MMAs)
+__device__ __forceinline__ unsigned elect_one_sync() {
+    unsigned pred = 0, laneid = 0;
+    asm volatile("{\n\t.reg .b32 %%rx;\n\t.reg .pred %%px;\n\telect.sync %%rx|%%px, %2;\n\t@%%px mov.s32 %1, 1;\n\tmov.s32 %0, %%rx;\n\t}\n"
+                 : "+r"(laneid), "+r"(pred) : "r"(0xFFFFFFFFu));
+    return pred;
+}
 __device__ __forceinline__ void umma_commit(unsigned mbar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(mbar) : "memory");
 }

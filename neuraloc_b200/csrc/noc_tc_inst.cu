@@ -4,13 +4,13 @@
 namespace noc {
 //                              kind NA CH minb
 #if NOC_TC_SHAPE == 0
-using Shape = TcShape<2, 1, 32, 1>;     // one quadcopter, d = 12 (singlequad: m = 128, one CTA per SM)
+using Shape = TcShape<2, 1, 32, 1, 2>;  // one quadcopter, d = 12 (singlequad: m = 128, one 8-warp CTA per SM, 2 threads per sample)
 #elif NOC_TC_SHAPE == 1
 using Shape = TcShape<0, 2, 16, 4>;     // Cross2D, 2 agents, d = 4 (softcorridor, swap2, hardcorridor)
 #elif NOC_TC_SHAPE == 2
 using Shape = TcShape<0, 4, 16, 3>;     // Cross2D, 4 agents, d = 8 (midcross4)
 #elif NOC_TC_SHAPE == 3
-using Shape = TcShape<0, 12, 16, 2>;    // Cross2D, 12 agents, d = 24 (swap12)
+using Shape = TcShape<0, 12, 16, 3>;    // Cross2D, 12 agents, d = 24 (swap12)
 #else
 #error "NOC_TC_SHAPE must be 0..3"
 #endif

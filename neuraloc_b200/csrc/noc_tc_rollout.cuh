@@ -25,7 +25,19 @@
 #include "noc_launch.cuh"
 #include "noc_tc.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
 namespace noc {
+
+// One entry per grad-Phi evaluation of a rollout, in execution order: the RK stages of every step (OCflow.py:157-184),
+// the control evaluation after each step when intermediates are requested (:51-55), and the terminal evaluation (:58).
+// Times and RK weights are the reference's python doubles rounded to fp32 once, on the host.
+struct __align__(16) TcEval {
+    float t, wgt, cnext, h;         // evaluation time, weight of this stage in the RK sum, coefficient of the next stage input, step
+    int k, kind, first, last;       // step index; 0 = RK stage, 1 = controls, 2 = terminal; first / last stage of its step
+};
 
 struct TcArgs {
     int m, mp;                      // hidden width and its padded value (multiple of the epilogue chunk)
@@ -36,7 +48,8 @@ struct TcArgs {
     const float* x;
     long long n;
     int nt, stepper, mode;
-    const double* times;
+    const TcEval* evals;            // flat sequence of Phi evaluations of one rollout (host-built, see tc_build_evals)
+    int nevals;
     float alph0, alph3, alph4, alph5, t_end;
     double* partials;
     float* out_a; float* out_b; float* out_c;
@@ -44,7 +57,7 @@ struct TcArgs {
 };
 
 // problem shapes the kernel is instantiated for
-template <int KIND_, int NA_, int CH_, int MINB_>
+template <int KIND_, int NA_, int CH_, int MINB_, int SPLIT_ = 1>
 struct TcShape {
     static constexpr int KIND = KIND_, NA = NA_;
     static constexpr int DIM = (KIND == 2) ? 12 : (KIND == 0 ? 2 : 3);
@@ -53,6 +66,8 @@ struct TcShape {
     static constexpr int NCTRL = (KIND == 2) ? 4 * NA : d;
     static constexpr int CH = CH_;                                 // epilogue chunk (TMEM columns per load)
     static constexpr int MINB = MINB_;
+    static constexpr int SPLIT = SPLIT_;                           // threads per sample: each owns 1/SPLIT of the hidden units in the epilogues
+    static constexpr int NT = 128 * SPLIT;
     static_assert(KIND != 2 || NA == 1, "one quadcopter");
 };
 
@@ -95,15 +110,16 @@ __device__ __forceinline__ void load_chunk3(const unsigned char* base, int plane
 }
 
 // one logical fp32 product block: six bf16 MMAs over the three planes of A and B (same descriptor geometry per plane);
-// hi*hi goes to `d_main`, the five correction products to `d_corr` (see the header)
-__device__ __forceinline__ void mma6(unsigned d_main, unsigned d_corr, unsigned a_addr, int a_plane, unsigned a_lbo, unsigned a_sbo,
-                                     unsigned b_addr, int b_plane, unsigned b_lbo, unsigned b_sbo, unsigned idesc, int accumulate) {
-    umma_bf16(d_main, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accumulate);                       // hh
-    umma_bf16(d_corr, umma_desc(a_addr + 2 * a_plane, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, accumulate);         // lh
-    umma_bf16(d_corr, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr + 2 * b_plane, b_lbo, b_sbo), idesc, 1);                  // hl
-    umma_bf16(d_corr, umma_desc(a_addr + a_plane, a_lbo, a_sbo), umma_desc(b_addr + b_plane, b_lbo, b_sbo), idesc, 1);            // mm
-    umma_bf16(d_corr, umma_desc(a_addr + a_plane, a_lbo, a_sbo), umma_desc(b_addr, b_lbo, b_sbo), idesc, 1);                      // mh
-    umma_bf16(d_corr, umma_desc(a_addr, a_lbo, a_sbo), umma_desc(b_addr + b_plane, b_lbo, b_sbo), idesc, 1);                      // hm
+// hi*hi goes to `d_main`, the five correction products to `d_corr` (see the header).  `ad` / `bd` are the descriptors of
+// the hi planes; the start-address field is the low 14 bits (16-byte units), so another plane or k-block is an integer add.
+__device__ __forceinline__ void mma6(unsigned d_main, unsigned d_corr, unsigned long long ad, unsigned a_plane16,
+                                     unsigned long long bd, unsigned b_plane16, unsigned idesc, int accumulate) {
+    umma_bf16(d_main, ad, bd, idesc, accumulate);                               // hh
+    umma_bf16(d_corr, ad + 2 * a_plane16, bd, idesc, accumulate);               // lh
+    umma_bf16(d_corr, ad, bd + 2 * b_plane16, idesc, 1);                        // hl
+    umma_bf16(d_corr, ad + a_plane16, bd + b_plane16, idesc, 1);                // mm
+    umma_bf16(d_corr, ad + a_plane16, bd, idesc, 1);                            // mh
+    umma_bf16(d_corr, ad, bd + b_plane16, idesc, 1);                            // hm
 }
 
 // v[0..CH) = [ta] + [tb]: two accumulators summed in round-to-nearest fp32, one wait for both loads
@@ -135,7 +151,7 @@ __device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
 // bytes of dynamic shared memory for (mp, KS)
 static inline size_t tc_smem_bytes(int mp, int KS) {
     return 3 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
-           sizeof(float) * (2 * (size_t)mp + KS + 32);
+           sizeof(float) * (2 * (size_t)mp + KS + 32 + 128);
 }
 static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) | terminal-only S.symb corr
     int need = 3 * std::max(mp, KS) + KS, c = 32;
@@ -144,10 +160,13 @@ static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) |
 }
 
 template <class SH>
-__global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs A) {
+__global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcArgs A) {
     constexpr int d = SH::d, D = SH::D, KS = SH::KS, NZ = SH::NZ, NCTRL = SH::NCTRL, CH = SH::CH, KIND = SH::KIND;
+    constexpr int SPLIT = SH::SPLIT, NT = SH::NT;
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5;
+    const int row = tid & 127, hf = tid >> 7;                  // my sample (= TMEM lane) and my share of the hidden units
+    const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the same value, known to the compiler as warp-uniform
     const int m = A.m, mp = A.mp;
     const ProbPack& pr = A.prob;
     // shared-memory map (bytes); every operand has three planes (hi, mid, lo)
@@ -162,26 +181,27 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
     float* sw = sb1 + mp;
     float* scw = sw + mp;                                // KS floats
     float* sred = scw + KS;                              // 4 warps x 8
+    float* sphi = sred + 32;                             // 128: partial w.u1 of the second thread of a sample (SPLIT = 2)
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned tmem_base_s;
 
     // ---- one-time per CTA: weights -> split bf16 operands in canonical layout (padded units have zero weights: they
     //      contribute exactly nothing to any contraction)
-    for (int i = tid; i < mp * (mp / 8); i += 128) {     // K1[o][k0..k0+8)
+    for (int i = tid; i < mp * (mp / 8); i += NT) {     // K1[o][k0..k0+8)
         const int o = i / (mp / 8), k0 = (i % (mp / 8)) * 8;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) v[e] = (o < m && k0 + e < m) ? A.K1[o * m + k0 + e] : 0.f;
         store_chunk3(sK1, pK1, o, k0, mp, v);
     }
-    for (int i = tid; i < mp * (KS / 8); i += 128) {     // K0b[j][k]: K0 | b0 | 0
+    for (int i = tid; i < mp * (KS / 8); i += NT) {     // K0b[j][k]: K0 | b0 | 0
         const int j = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) { const int k = k0 + e; v[e] = (j >= m) ? 0.f : ((k < D) ? A.K0[j * D + k] : (k == D ? A.b0[j] : 0.f)); }
         store_chunk3(sK0, pK0, j, k0, KS, v);
     }
-    for (int i = tid; i < KS * (KS / 8); i += 128) {     // symb[n = k'][k]: (A'A)[k][k'] | c_w[k'] in column D | 0
+    for (int i = tid; i < KS * (KS / 8); i += NT) {     // symb[n = k'][k]: (A'A)[k][k'] | c_w[k'] in column D | 0
         const int kp = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
         float v[8];
 #pragma unroll
@@ -194,7 +214,7 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
         }
         store_chunk3(sSy, pSy, kp, k0, KS, v);
     }
-    for (int i = tid; i < mp; i += 128) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] : 0.f; }
+    for (int i = tid; i < mp; i += NT) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] : 0.f; }
     if (tid < KS) scw[tid] = (tid < D) ? A.c_w[tid] : 0.f;
     if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), A.tmem_cols);
     if (tid == 0) mbar_init(smem_u32(&mbar), 1);
@@ -207,149 +227,54 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
     const unsigned tcor = tacc + C;                      // correction-term accumulator, same column map
     const unsigned tT0 = tacc + 2 * C;                   // tanh(o); at the terminal evaluation also S.symb' (main)
     const unsigned tTq = tacc + 3 * C;                   // terminal evaluation only: S.symb' (corrections), KS columns
-    const unsigned lane_bits = (unsigned)(warp * 32) << 16;
+    const unsigned lane_bits = (unsigned)((warp & 3) * 32) << 16;
     const unsigned mb = smem_u32(&mbar);
     int phase = 0;
     const unsigned idesc_m_k = umma_idesc_bf16(128, mp, 0), idesc_m_mn = umma_idesc_bf16(128, mp, 1);
     const unsigned idesc_s_mn = umma_idesc_bf16(128, KS, 1), idesc_s_k = umma_idesc_bf16(128, KS, 0);
-    const unsigned aX = smem_u32(sX), aS = smem_u32(sS), aK1 = smem_u32(sK1), aK0 = smem_u32(sK0), aSy = smem_u32(sSy);
     const unsigned sboM = (unsigned)(mp >> 3) * 128;     // 8-row-group stride of an operand with K = mp
     constexpr unsigned sboS = (unsigned)(KS >> 3) * 128; // ... with K = KS
+    // hi-plane descriptors (k-block 0); planes and k-blocks are reached by adding 16-byte-unit offsets
+    const unsigned long long dX = umma_desc(smem_u32(sX), 128, sboM), dS = umma_desc(smem_u32(sS), 128, sboS);
+    const unsigned long long dK1k = umma_desc(smem_u32(sK1), 128, sboM), dK1n = umma_desc(smem_u32(sK1), sboM, 128);
+    const unsigned long long dK0k = umma_desc(smem_u32(sK0), 128, sboS), dK0n = umma_desc(smem_u32(sK0), sboS, 128);
+    const unsigned long long dSy = umma_desc(smem_u32(sSy), 128, sboS);
+    const unsigned qX = pX >> 4, qS = pS >> 4, qK1 = pK1 >> 4, qK0 = pK0 >> 4, qSy = pSy >> 4;    // plane strides, 16-byte units
+    const unsigned kK1n = (2 * sboM) >> 4;               // k-block step of K1 read MN-major (16 rows)
+    constexpr unsigned kK0n = (2 * sboS) >> 4;           // ... of K0b read MN-major
 
-    // publish my operand writes, let thread 0 issue `issue`, wait for the tensor core
-    auto run_mma = [&](auto issue) {
+    // publish my operand writes and let thread 0 issue `issue`; mma_wait() then blocks until the tensor core is done
+    auto mma_issue = [&](auto issue) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (tid == 0) {
-            tc_fence_after();
-            issue();
-            umma_commit(mb);
+        if (warp_u == 0) {                               // warp-uniform branch, then one elected lane
+            if (elect_one_sync()) {
+                tc_fence_after();
+                issue();
+                umma_commit(mb);
+            }
+            __syncwarp();
         }
+    };
+    auto mma_wait = [&] {
         mbar_wait(mb, phase);
         phase ^= 1;
         tc_fence_after();
     };
+    auto run_mma = [&](auto issue) { mma_issue(issue); mma_wait(); };
 
-    // grad Phi at s = [xs, t] -> g[0..D); terminal: also Phi(s)
-    auto chain = [&](const float (&xs)[d], float t, float (&g)[KS], bool terminal, float& phi_out) {
-#pragma unroll
-        for (int c0 = 0; c0 < KS; c0 += 8) {             // S operand row: [x, t, 1, 0..]
-            float v[8];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = (k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f)); }
-            store_chunk3(sS, pS, tid, c0, KS, v);
-        }
-        run_mma([&] {                                    // GEMM-1: O = S . K0b'
-#pragma unroll
-            for (int kb = 0; kb < KS / 16; ++kb)
-                mma6(tacc, tcor, aS + kb * 256, pS, 128, sboS, aK0 + kb * 256, pK0, 128, sboS, idesc_m_k, kb > 0);
-        });
-        for (int c0 = 0; c0 < mp; c0 += CH) {            // u0 = act(o) -> X operand, tanh(o) -> TMEM
-            float v[CH], tt[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) act_tanh(v[i], v[i], tt[i]);
-            tmem_st<CH>(tT0 + lane_bits + c0, tt);
-#pragma unroll
-            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
-        }
-        run_mma([&] {                                    // GEMM-2: A1 = U0 . K1'  (B K-major)
-            for (int kb = 0; kb < mp / 16; ++kb)
-                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK1 + kb * 256, pK1, 128, sboM, idesc_m_k, kb > 0);
-        });
-        float phiN = 0.f;
-        for (int c0 = 0; c0 < mp; c0 += CH) {            // y = tanh(a1 + b1) * w -> X operand
-            float v[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
-#pragma unroll
-            for (int q = 0; q < CH / 8; ++q) {
-                float u8[8];
-                if (terminal) load_chunk3(sX, pX, tid, c0 + q * 8, mp, u8);      // u0, before it is overwritten
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int col = c0 + q * 8 + e;
-                    const float pre = v[q * 8 + e] + sb1[col], wv = sw[col];
-                    if (terminal) {
-                        float av, tv;
-                        act_tanh(pre, av, tv);
-                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);
-                        v[q * 8 + e] = tv * wv;
-                    } else {
-                        v[q * 8 + e] = tanh_only(pre) * wv;
-                    }
-                }
-                store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
-            }
-        }
-        run_mma([&] {                                    // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
-            for (int kb = 0; kb < mp / 16; ++kb)
-                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK1 + kb * 2 * sboM, pK1, sboM, 128, idesc_m_mn, kb > 0);
-        });
-        for (int c0 = 0; c0 < mp; c0 += CH) {            // v = tanh(o) * (w + h z1acc) -> X operand
-            float v[CH], tt[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
-            tmem_ld<CH>(tT0 + lane_bits + c0, tt);
-#pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = tt[i] * (sw[c0 + i] + A.h * v[i]);
-#pragma unroll
-            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, tid, c0 + q * 8, mp, v + q * 8);
-        }
-        run_mma([&] {                                    // GEMM-4: G = V . K0b (MN-major view) + S . symb'
-            for (int kb = 0; kb < mp / 16; ++kb)
-                mma6(tacc, tcor, aX + kb * 256, pX, 128, sboM, aK0 + kb * 2 * sboS, pK0, sboS, 128, idesc_s_mn, kb > 0);
-            // the terminal evaluation needs S.symb' on its own (Phi's quadratic term): it goes to the free tanh columns
-            const unsigned qm = terminal ? tT0 : tacc, qc = terminal ? tTq : tcor;
-#pragma unroll
-            for (int kb = 0; kb < KS / 16; ++kb)
-                mma6(qm, qc, aS + kb * 256, pS, 128, sboS, aSy + kb * 256, pSy, 128, sboS, idesc_s_k, terminal ? (kb > 0) : 1);
-        });
-#pragma unroll
-        for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tacc + lane_bits + c0, tcor + lane_bits + c0, g + c0);
-        if (terminal) {                                   // Phi = w.u1 + 0.5 s'A'A s + c_w.s + c_b  (Phi.py:96)
-            float gq[KS];
-#pragma unroll
-            for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tT0 + lane_bits + c0, tTq + lane_bits + c0, gq + c0);
-            float quad = 0.f, lin = 0.f;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                const float sv = (k < d) ? xs[k < d ? k : 0] : t;
-                quad = fmaf(sv, gq[k] - scw[k], quad);   // gq carries c_w (column D of symb)
-                lin = fmaf(scw[k], sv, lin);
-                g[k] += gq[k];
-            }
-            phi_out = phiN + 0.5f * quad + (lin + A.c_b[0]);
-        }
-    };
-
-    // calcLHQW / calcGradpH / calcCtrls in registers: dx = -grad_p H, cost rates L, HJ = |Phi_t - H|, Q, W; uctrl = the
-    // quadcopter thrust (Cross2D.py:69-87,133-165; Quadcopter.py:65-113,160-197)
-    auto problem = [&](const float (&x)[d], const float (&g)[KS], float (&dx)[d], float (&rate)[4], float& uctrl) {
+    // calcLHQW / calcGradpH / calcCtrls in registers, in two parts (Cross2D.py:69-87,133-165; Quadcopter.py:65-113,160-197).
+    // Part 1 needs only x and runs while GEMM-1 is in flight: the terrain and interaction costs (q, w) of Cross2D, or the
+    // thrust direction (f7, f8, f9) of the quadcopter, returned in xq[0..3).
+    auto problem_x = [&](const float (&x)[d], float (&xq)[3]) {
         if constexpr (KIND == 2) {
             float sps, cps, sth, cth, sph, cph;
             sincosf(x[3], &sps, &cps); sincosf(x[4], &sth, &cth); sincosf(x[5], &sph, &cph);
-            const float f7 = sps * sph + cps * sth * cph, f8 = -cps * sph + sps * sth * cph, f9 = cth * cph;
-            const float fp = f7 * g[6] + f8 * g[7] + f9 * g[8];
-            const float u = float(-1.0 / (2.0 * pr.mass)) * fp;
-            const float sq = g[9] * g[9] + g[10] * g[10] + g[11] * g[11];
-            float L = float(pr.alph_Q) * 0.f;
-            L = L + 2.f + u * u + 0.25f * sq;
-            const float um = u / float(pr.mass);
-            const float xv = x[6] * g[0] + x[7] * g[1] + x[8] * g[2];
-            const float xw = x[9] * g[3] + x[10] * g[4] + x[11] * g[5];
-            const float H = 0.f - L - xv - xw - um * fp + float(pr.grav) * g[8] + 0.5f * sq;
-            rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = 0.f; rate[3] = 0.f;
-#pragma unroll
-            for (int c = 0; c < 6; ++c) dx[c] = x[6 + c];
-            dx[6] = -(-um * f7); dx[7] = -(-um * f8); dx[8] = -(-um * f9 + float(pr.grav));
-#pragma unroll
-            for (int c = 9; c < 12; ++c) dx[c] = -(0.5f * g[c]);
-            uctrl = u;
+            xq[0] = sps * sph + cps * sth * cph; xq[1] = -cps * sph + sps * sth * cph; xq[2] = cth * cph;
         } else {
             constexpr int NA = SH::NA, DIM = SH::DIM;
-            float pp = 0.f, q = 0.f, w = 0.f;
-#pragma unroll
-            for (int r = 0; r < d; ++r) pp = fmaf(g[r], g[r], pp);
+            float q = 0.f, w = 0.f;
             if ((pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0)) {
 #pragma unroll
                 for (int a = 0; a < NA; ++a) q += terrain_agent<float>(pr, x[a * DIM], x[a * DIM + 1], DIM == 3 ? x[a * DIM + DIM - 1] : 0.f);
@@ -393,6 +318,126 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
                     }
                 }
             }
+            xq[0] = q; xq[1] = w; xq[2] = 0.f;
+        }
+    };
+    // grad Phi at s = [xs, t]; problem_x(xs) runs between the issue of GEMM-1 and the wait for it
+    const int cbeg = hf * (mp / SPLIT), cend = cbeg + mp / SPLIT;      // my hidden units
+    auto chain = [&](const float (&xs)[d], float t, float (&g)[KS], bool terminal, float& phi_out, float (&xq)[3]) {
+#pragma unroll
+        for (int c0 = 0; c0 < KS; c0 += 8) {             // S operand row: [x, t, 1, 0..]
+            if (SPLIT > 1 && ((c0 >> 3) % SPLIT) != hf) continue;
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = (k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f)); }
+            store_chunk3(sS, pS, row, c0, KS, v);
+        }
+        mma_issue([&] {                                  // GEMM-1: O = S . K0b'
+#pragma unroll
+            for (int kb = 0; kb < KS / 16; ++kb) mma6(tacc, tcor, dS + kb * 16, qS, dK0k + kb * 16, qK0, idesc_m_k, kb > 0);
+        });
+        if (!terminal) problem_x(xs, xq);
+        mma_wait();
+        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // u0 = act(o) -> X operand, tanh(o) -> TMEM
+            float v[CH], tt[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) act_tanh(v[i], v[i], tt[i]);
+            tmem_st<CH>(tT0 + lane_bits + c0, tt);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+        }
+        run_mma([&] {                                    // GEMM-2: A1 = U0 . K1'  (B K-major)
+            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1k + kb * 16, qK1, idesc_m_k, kb > 0);
+        });
+        float phiN = 0.f;
+        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // y = tanh(a1 + b1) * w -> X operand
+            float v[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) {
+                float u8[8];
+                if (terminal) load_chunk3(sX, pX, row, c0 + q * 8, mp, u8);      // u0, before it is overwritten
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int col = c0 + q * 8 + e;
+                    const float pre = v[q * 8 + e] + sb1[col], wv = sw[col];
+                    if (terminal) {
+                        float av, tv;
+                        act_tanh(pre, av, tv);
+                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);
+                        v[q * 8 + e] = tv * wv;
+                    } else {
+                        v[q * 8 + e] = tanh_only(pre) * wv;
+                    }
+                }
+                store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+            }
+        }
+        if (SPLIT > 1 && terminal && hf == 1) sphi[row] = phiN;
+        run_mma([&] {                                    // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
+            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1n + kb * kK1n, qK1, idesc_m_mn, kb > 0);
+        });
+        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // v = tanh(o) * (w + h z1acc) -> X operand
+            float v[CH], tt[CH];
+            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+            tmem_ld<CH>(tT0 + lane_bits + c0, tt);
+#pragma unroll
+            for (int i = 0; i < CH; ++i) v[i] = tt[i] * (sw[c0 + i] + A.h * v[i]);
+#pragma unroll
+            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+        }
+        run_mma([&] {                                    // GEMM-4: G = V . K0b (MN-major view) + S . symb'
+            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK0n + kb * kK0n, qK0, idesc_s_mn, kb > 0);
+            // the terminal evaluation needs S.symb' on its own (Phi's quadratic term): it goes to the free tanh columns
+            const unsigned qm = terminal ? tT0 : tacc, qc = terminal ? tTq : tcor;
+#pragma unroll
+            for (int kb = 0; kb < KS / 16; ++kb) mma6(qm, qc, dS + kb * 16, qS, dSy + kb * 16, qSy, idesc_s_k, terminal ? (kb > 0) : 1);
+        });
+#pragma unroll
+        for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tacc + lane_bits + c0, tcor + lane_bits + c0, g + c0);
+        if (terminal) {                                   // Phi = w.u1 + 0.5 s'A'A s + c_w.s + c_b  (Phi.py:96)
+            float gq[KS];
+#pragma unroll
+            for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tT0 + lane_bits + c0, tTq + lane_bits + c0, gq + c0);
+            float quad = 0.f, lin = 0.f;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const float sv = (k < d) ? xs[k < d ? k : 0] : t;
+                quad = fmaf(sv, gq[k] - scw[k], quad);   // gq carries c_w (column D of symb)
+                lin = fmaf(scw[k], sv, lin);
+                g[k] += gq[k];
+            }
+            if (SPLIT > 1) phiN += sphi[row];             // written before GEMM-3's barrier; only the hf = 0 thread's sum is used
+            phi_out = phiN + 0.5f * quad + (lin + A.c_b[0]);
+        }
+    };
+
+    // Part 2, after grad Phi: dx = -grad_p H, cost rates L, HJ = |Phi_t - H|, Q, W; uctrl = the quadcopter thrust
+    auto problem = [&](const float (&x)[d], const float (&g)[KS], const float (&xq)[3], float (&dx)[d], float (&rate)[4], float& uctrl) {
+        if constexpr (KIND == 2) {
+            const float f7 = xq[0], f8 = xq[1], f9 = xq[2];
+            const float fp = f7 * g[6] + f8 * g[7] + f9 * g[8];
+            const float u = float(-1.0 / (2.0 * pr.mass)) * fp;
+            const float sq = g[9] * g[9] + g[10] * g[10] + g[11] * g[11];
+            float L = float(pr.alph_Q) * 0.f;
+            L = L + 2.f + u * u + 0.25f * sq;
+            const float um = u / float(pr.mass);
+            const float xv = x[6] * g[0] + x[7] * g[1] + x[8] * g[2];
+            const float xw = x[9] * g[3] + x[10] * g[4] + x[11] * g[5];
+            const float H = 0.f - L - xv - xw - um * fp + float(pr.grav) * g[8] + 0.5f * sq;
+            rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = 0.f; rate[3] = 0.f;
+#pragma unroll
+            for (int c = 0; c < 6; ++c) dx[c] = x[6 + c];
+            dx[6] = -(-um * f7); dx[7] = -(-um * f8); dx[8] = -(-um * f9 + float(pr.grav));
+#pragma unroll
+            for (int c = 9; c < 12; ++c) dx[c] = -(0.5f * g[c]);
+            uctrl = u;
+        } else {
+            float pp = 0.f, w = xq[1];
+            const float q = xq[0];
+#pragma unroll
+            for (int r = 0; r < d; ++r) pp = fmaf(g[r], g[r], pp);
             float Qret, L;
             if (pr.kind == 0) { Qret = float(pr.alph_Q) * q; L = 0.5f * pp + Qret; }     // Cross2D returns Q pre-scaled (quirk 6)
             else { Qret = (pr.alph_Q > 0.0) ? q : 0.f; L = 0.5f * pp + float(pr.alph_Q) * Qret; }
@@ -407,53 +452,44 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
 
     double csum[7] = {0, 0, 0, 0, 0, 0, 0};
     long long cnt = 0;
-    const int nstage = (A.stepper == 4) ? 4 : (A.stepper == 1 ? 1 : 0);
     const bool inter = (A.mode == 2);
     const int ntp1 = A.nt + 1;
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const long long s0 = (long long)tile * 128;
         const int nvalid = (int)((A.n - s0 < 128) ? (A.n - s0) : 128);
-        const bool valid = tid < nvalid;
-        const long long gs = s0 + (valid ? tid : nvalid - 1);        // padding threads replay the last valid sample
+        const bool valid = row < nvalid;
+        const bool writer = valid && hf == 0;                          // one thread per sample writes results
+        const long long gs = s0 + (valid ? row : nvalid - 1);        // padding threads replay the last valid sample
         float z0[NZ], za[NZ];
 #pragma unroll
         for (int c = 0; c < d; ++c) z0[c] = A.x[gs * d + c];
 #pragma unroll
         for (int c = d; c < NZ; ++c) z0[c] = 0.f;
-        if (inter && valid) {                                          // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
+        if (inter && writer) {                                         // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
 #pragma unroll
             for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1] = z0[c];
 #pragma unroll
             for (int c = 0; c < NCTRL; ++c) A.out_c[(gs * NCTRL + c) * ntp1] = 0.f;
         }
-        // ONE call site for the chain: the nt * (stages [+ 1 control evaluation]) + 1 terminal evaluations of a tile are a
-        // flat sequence; `xs` always holds the next evaluation's input.
+        // ONE call site for the chain: the evaluations of a rollout are a flat host-built sequence (TcEval); `xs` always
+        // holds the next evaluation's input.
         float g[KS], dx[d], xs[d], phi1 = 0.f;
 #pragma unroll
         for (int c = 0; c < d; ++c) xs[c] = z0[c];
-        const int per = nstage + (inter ? 1 : 0);
-        const int total = A.nt * per + 1;
-        for (int it = 0; it < total; ++it) {
-            const bool term = (it == total - 1);
-            const int k = term ? 0 : it / per, st = term ? 0 : it % per;
-            const bool ctl = !term && st == nstage;                 // control evaluation after the step (OCflow.py:51-55)
-            const double* tt = A.times + 5 * k;
-            const float hstep = float(tt[4]);                       // h = t1 - t0 recomputed per step (OCflow.py:169)
-            float wgt = 1.f, cnext = 0.f, tcur = float(tt[0]);
-            if (term) tcur = A.t_end;
-            else if (ctl) tcur = float(tt[3]);                      // new state, OLD time (quirk 3)
-            else if (nstage == 4) {                                 // RK4 weights (OCflow.py:172-182)
-                if (st == 0) { wgt = float(1.0 / 6.0); cnext = 0.5f; }
-                else if (st == 1) { wgt = float(2.0 / 6.0); cnext = 0.5f; tcur = float(tt[1]); }
-                else if (st == 2) { wgt = float(2.0 / 6.0); cnext = 1.0f; tcur = float(tt[1]); }
-                else { wgt = float(1.0 / 6.0); tcur = float(tt[2]); }
-            }
-            chain(xs, tcur, g, term, phi1);
+        const float4* etab = reinterpret_cast<const float4*>(A.evals);
+        for (int it = 0; it < A.nevals; ++it) {
+            const float4 ef = __ldg(etab + 2 * it);
+            const int4 ei = __ldg(reinterpret_cast<const int4*>(etab + 2 * it + 1));
+            const float tcur = ef.x, wgt = ef.y, cnext = ef.z, hstep = ef.w;
+            const int k = ei.x, kind = ei.y, first = ei.z, last = ei.w;
+            const bool term = (kind == 2);
+            float xq[3];
+            chain(xs, tcur, g, term, phi1, xq);
             if (term) break;
             float rate[4], uc;
-            problem(xs, g, dx, rate, uc);
-            if (ctl) {
-                if (valid) {
+            problem(xs, g, xq, dx, rate, uc);
+            if (kind == 1) {                                         // controls at the new state, OLD time (quirk 3)
+                if (writer) {
 #pragma unroll
                     for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1 + (k + 1)] = z0[c];
                     if constexpr (KIND == 2) {
@@ -468,14 +504,14 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
                 continue;
             }
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) {
+            for (int c = 0; c < NZ; ++c) {                           // RK combination (OCflow.py:143-184)
                 float kk;
                 if (c < d) kk = (KIND == 2) ? hstep * dx[c < d ? c : 0] : hstep * (-g[c]);
                 else kk = hstep * rate[c >= d ? c - d : 0];
-                za[c] = ((st == 0) ? z0[c] : za[c]) + wgt * kk;
+                za[c] = (first ? z0[c] : za[c]) + wgt * kk;
                 if (c < d) dx[c < d ? c : 0] = kk;
             }
-            if (st != nstage - 1) {
+            if (!last) {
 #pragma unroll
                 for (int c = 0; c < d; ++c) xs[c] = z0[c] + cnext * dx[c];
             } else {
@@ -503,7 +539,7 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
                 float v = valid ? cost[q] : 0.f;
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if ((tid & 31) == 0) sred[warp * 8 + q] = v;
+                if ((tid & 31) == 0 && hf == 0) sred[warp * 8 + q] = v;
             }
             __syncthreads();
             if (tid == 0) {
@@ -511,7 +547,7 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
                 cnt += nvalid;
             }
             __syncthreads();
-        } else if (A.mode == 1 && valid) {
+        } else if (A.mode == 1 && writer) {
             float* o = A.out_a + gs * 8;
             o[0] = cost[0] + A.alph0 * cost[1] + A.alph3 * cost[2] + A.alph4 * cost[3] + A.alph5 * cost[4];   // OCflow.py:75
 #pragma unroll
@@ -527,25 +563,68 @@ __global__ void __launch_bounds__(128, SH::MINB) rollout_tc_kernel(const TcArgs 
     if (warp == 0) tmem_dealloc(tacc, A.tmem_cols);
 }
 
+// host: the flat evaluation sequence of one rollout from the stage-time table (nt x 5 doubles, noc_stage_times)
+static inline void tc_build_evals(const double* tab, int nt, int stepper, bool inter, double t_end, std::vector<TcEval>& ev) {
+    const int nstage = (stepper == NOC_STEP_RK4) ? 4 : (stepper == NOC_STEP_RK1 ? 1 : 0);
+    ev.clear();
+    for (int k = 0; k < nt; ++k) {
+        const double* tt = tab + 5 * k;
+        for (int st = 0; st < nstage; ++st) {
+            TcEval e;
+            e.h = (float)tt[4]; e.k = k; e.kind = 0; e.first = (st == 0); e.last = (st == nstage - 1);
+            e.t = (float)tt[0]; e.wgt = 1.f; e.cnext = 0.f;
+            if (nstage == 4) {                                      // OCflow.py:172-182
+                const double w[4] = {1.0 / 6.0, 2.0 / 6.0, 2.0 / 6.0, 1.0 / 6.0}, c[4] = {0.5, 0.5, 1.0, 0.0};
+                const double ts[4] = {tt[0], tt[1], tt[1], tt[2]};
+                e.t = (float)ts[st]; e.wgt = (float)w[st]; e.cnext = (float)c[st];
+            }
+            ev.push_back(e);
+        }
+        if (inter) {
+            TcEval e;
+            e.t = (float)tt[3]; e.wgt = 0.f; e.cnext = 0.f; e.h = (float)tt[4]; e.k = k; e.kind = 1; e.first = 0; e.last = 0;
+            ev.push_back(e);
+        }
+    }
+    TcEval e;
+    e.t = (float)t_end; e.wgt = 0.f; e.cnext = 0.f; e.h = 0.f; e.k = 0; e.kind = 2; e.first = 0; e.last = 0;
+    ev.push_back(e);
+}
+
 template <class SH>
 int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     const size_t smem = tc_smem_bytes(A.mp, SH::KS);
     auto kern = rollout_tc_kernel<SH>;
     if (smem + 1024 > (size_t)smem_limit) return fail(NOC_ERR_NOMEM, "tensor-core rollout needs %zu B of shared memory", smem);
     NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 0;
-    NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 128, smem));
+    // resident CTAs per SM from the kernel's own resource use (registers, shared memory incl. the 1 KB the driver reserves
+    // per block, TMEM columns: a CTA that cannot get its columns would only wait in tcgen05.alloc)
+    int occ_api = 0;
+    NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_api, kern, SH::NT, smem));
+    cudaFuncAttributes fa;
+    NOC_CUDA(cudaFuncGetAttributes(&fa, kern));
+    int dev = 0, regs_sm = 65536, smem_sm = 233472;
+    NOC_CUDA(cudaGetDevice(&dev));
+    NOC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
+    NOC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
     A.tmem_cols = tc_tmem_cols(A.mp, SH::KS);
-    per_sm = std::min(per_sm, 512 / A.tmem_cols);       // a CTA that cannot get its TMEM columns would only wait
+    const int by_regs = regs_sm / (align_up(std::max(fa.numRegs, 1), 8) * SH::NT);
+    const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
+    int per_sm = std::min(std::min(by_regs, by_smem), 512 / A.tmem_cols);
+    if (getenv("NOC_DEBUG"))
+        fprintf(stderr, "[noc] tc occupancy: api=%d regs=%d (->%d) smem->%d tmem->%d\n", occ_api, fa.numRegs, by_regs, by_smem, 512 / A.tmem_cols);
     if (per_sm < 1) return fail(NOC_ERR_NOMEM, "tensor-core rollout does not fit on an SM");
     A.ntiles = (int)((A.n + 127) / 128);
     const int grid = std::max(1, std::min(A.ntiles, per_sm * sm_count()));
+    if (getenv("NOC_DEBUG"))
+        fprintf(stderr, "[noc] tc rollout: mp=%d KS=%d smem=%zu tmem_cols=%d CTAs/SM=%d grid=%d tiles=%d\n", A.mp, SH::KS, smem,
+                A.tmem_cols, per_sm, grid, A.ntiles);
     double* partials = nullptr;
     if (A.mode == NOC_MODE_MEAN) {
         NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)grid, st));
         A.partials = partials;
     }
-    kern<<<grid, 128, smem, st>>>(A);
+    kern<<<grid, SH::NT, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
     if (partials) {

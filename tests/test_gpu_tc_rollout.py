@@ -113,10 +113,25 @@ def test_tc_random_nets_any_width(nb, data, m, monkeypatch):
         _vs_tile(nb, monkeypatch, net, prob, x.cuda(), alph, 6, d, True)
 
 
-def test_tc_is_selected_only_where_it_applies(nb, monkeypatch):
-    """NOC_FORCE_PATH=tc on a shape the kernel is not written for falls back to the normal choice (still CUDA)."""
-    net, prob, xinit, meta = product_setup("softcorridor", torch.float32)
-    before = nb._cabi.lib().noc_launch_count()
+def test_path_selection(nb, monkeypatch):
+    """Default choice by shape and batch size (noc_last_path): tensor-core kernel for the shapes it is written for at
+    batch sizes above the small-batch threshold, NOC_TC=0 keeps the FMA tile kernel, other shapes are unaffected, and
+    NOC_FORCE_PATH=tc on a shape the kernel is not written for falls back to the normal choice (still CUDA)."""
+    monkeypatch.delenv("NOC_FORCE_PATH", raising=False)
+    net, prob, xinit, meta = product_setup("swap12", torch.float32)
+    x = xinit + 0.1 * torch.randn(1000, 24, device="cuda")
     with torch.no_grad():
-        Jc, cs = nb.OCflow(xinit, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
-    assert nb._cabi.lib().noc_launch_count() > before and np.isfinite(float(Jc))
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
+        assert nb._cabi.last_path() == "tensor"
+        nb.OCflow(x[:8].contiguous(), net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
+        assert nb._cabi.last_path() == "sample"
+        monkeypatch.setenv("NOC_TC", "0")
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
+        assert nb._cabi.last_path() == "tile"
+        monkeypatch.delenv("NOC_TC")
+        nb.OCflow(x.double(), net.double(), product_setup("swap12", torch.float64)[1], [0.0, 1.0], 4, "rk4", meta["alph"])
+        assert nb._cabi.last_path() == "tile"                      # fp64 has no tensor-core kernel
+        monkeypatch.setenv("NOC_FORCE_PATH", "tc")
+        net5, prob5, xinit5, meta5 = product_setup("swarm50", torch.float32)
+        Jc, cs = nb.OCflow(xinit5.repeat(300, 1), net5, prob5, [0.0, 1.0], 4, "rk4", meta5["alph"])
+        assert nb._cabi.last_path() == "tile" and np.isfinite(float(Jc))
