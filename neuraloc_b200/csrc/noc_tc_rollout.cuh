@@ -151,7 +151,7 @@ __device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
 // bytes of dynamic shared memory for (mp, KS)
 static inline size_t tc_smem_bytes(int mp, int KS) {
     return 3 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
-           sizeof(float) * (2 * (size_t)mp + KS + 32 + 128);
+           sizeof(float) * (2 * (size_t)mp + KS + 32 + 3 * 128);
 }
 static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) | terminal-only S.symb corr
     int need = 3 * std::max(mp, KS) + KS, c = 32;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     float* sw = sb1 + mp;
     float* scw = sw + mp;                                // KS floats
     float* sred = scw + KS;                              // 4 warps x 8
-    float* sphi = sred + 32;                             // 128: partial w.u1 of the second thread of a sample (SPLIT = 2)
+    float* sphi = sred + 32;                             // (SPLIT - 1) x 128: partial w.u1 of the other threads of a sample
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned tmem_base_s;
 
@@ -374,7 +374,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
                 store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
             }
         }
-        if (SPLIT > 1 && terminal && hf == 1) sphi[row] = phiN;
+        if (SPLIT > 1 && terminal && hf > 0) sphi[(hf - 1) * 128 + row] = phiN;
         run_mma([&] {                                    // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
             for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1n + kb * kK1n, qK1, idesc_m_mn, kb > 0);
         });
@@ -408,7 +408,10 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
                 lin = fmaf(scw[k], sv, lin);
                 g[k] += gq[k];
             }
-            if (SPLIT > 1) phiN += sphi[row];             // written before GEMM-3's barrier; only the hf = 0 thread's sum is used
+            if (SPLIT > 1) {                              // written before GEMM-3's barrier; only the hf = 0 thread's sum is used
+#pragma unroll
+                for (int q = 1; q < SPLIT; ++q) phiN += sphi[(q - 1) * 128 + row];
+            }
             phi_out = phiN + 0.5f * quad + (lin + A.c_b[0]);
         }
     };
