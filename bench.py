@@ -43,10 +43,15 @@ WORKLOADS = {
 
 
 # DRAM bytes per sample of the rollout kernel (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full`
-# capture, divided by the samples of that launch): profiles/r01_<workload>_ncu_summary.txt.  The algorithmic figure is
-# 4 d bytes per sample (the initial state is read once; mean mode writes nothing per sample).
-DRAM_BYTES_PER_SAMPLE = {"swap12": (12.838656e6 + 1.28e6) / 131072, "swarm50": (14.534144e6 + 1.083904e6) / 16384,
-                         "singlequad": (6.871808e6 + 294.912e6) / 131072}
+# capture, divided by the samples of that launch): profiles/r01_<workload>_<kernel>_ncu_summary.txt.  The algorithmic
+# figure is 4 d bytes per sample (the initial state is read once; mean mode writes nothing per sample); the excess is
+# register-spill / scratch-state write-back, negligible against the kernel's duration (compute-bound).
+DRAM_BYTES_PER_SAMPLE = {
+    ("swap12", "tensor"): (27.438336e6 + 78.08e6) / 262144,
+    ("singlequad", "tensor"): (12.780544e6 + 42.496e6) / 262144,
+    ("swap12", "tile"): (12.819456e6 + 256.0e6) / 131072,
+    ("swarm50", "tile"): (14.542336e6 + 1.271296e6) / 16384,
+}
 
 
 def tensor_flops_per_sample_step(d, m):
@@ -62,7 +67,7 @@ def roofline(workload, W, d, meta, n, nt, fl, step_s, fma_peak, path):
     live.  Tensor-core kernel: the bf16 flops it executes against MEASURED_PEAKS.json's sustained dense bf16 figure; the
     algorithmic (fp32-equivalent) rate and the FMA peak stay alongside, since that ratio is what the kernel replaces."""
     alg = n * nt * fl / step_s / 1e12
-    traffic = DRAM_BYTES_PER_SAMPLE[workload] * n if workload in DRAM_BYTES_PER_SAMPLE else None
+    traffic = DRAM_BYTES_PER_SAMPLE[(workload, path)] * n if (workload, path) in DRAM_BYTES_PER_SAMPLE else None
     note = ("DRAM bytes per launch = measured bytes per sample of the ncu capture in profiles/ x samples; "
             "algorithmic = %d bytes (4 d per sample)" % (4 * d * n))
     if path == "tensor":

@@ -10,7 +10,8 @@ bash scripts/gpu_prof.sh ${TAG}_tc singlequad 262144 rollout_tc_kernel 1
 bash scripts/gpu_prof.sh ${TAG}_fma swap12 131072 rollout_kernel 0
 bash scripts/gpu_prof.sh ${TAG}_fma swarm50 16384 rollout_kernel 1
 timeout 600 ncu --set full --import-source on --clock-control none -k regex:rollout_vec_kernel -s 2 -c 1 -f -o gpurun_out/prof_vec_swap12_$TAG python bench.py --latency --workload swap12 > gpurun_out/ncu_vec_$TAG.log 2>&1
-for W in softcorridor swap2 singlequad swarm50; do timeout 300 python bench.py --steps 2 --warmup 3 --workload $W --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_${W}_$TAG.json; done
+for W in softcorridor swap2 singlequad; do timeout 300 python bench.py --steps 2 --warmup 3 --workload $W --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_${W}_$TAG.json; done
+timeout 300 python bench.py --steps 2 --warmup 3 --workload swarm50 --samples 65536 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_swarm50_$TAG.json
 for W in swap12 softcorridor swap2 singlequad; do NOC_TC=0 timeout 300 python bench.py --steps 2 --warmup 3 --workload $W --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_${W}_fma_$TAG.json; done
 python scripts/peaks.py > gpurun_out/peaks_$TAG.txt 2>&1
 cat gpurun_out/BENCH_default_$TAG.json | cut -c1-1800; cat gpurun_out/BENCH_reference_$TAG.json | cut -c1-600; cat gpurun_out/peaks_$TAG.txt

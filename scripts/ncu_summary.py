@@ -14,7 +14,10 @@ keys = ["gpu__time_duration.sum", "launch__registers_per_thread", "launch__grid_
         "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
         "smsp__inst_executed.sum", "smsp__inst_executed_op_shared_ld.sum", "smsp__inst_executed_op_shared_st.sum",
         "smsp__inst_executed_op_global_ld.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct",
-        "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+        "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__inst_executed_pipe_tc.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_tmem.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active"]
+keys += [k for k in m if "pipe_tensor" in k and ("cycles_active" in k) and ("hmma" in k or k.endswith("pct_of_peak_sustained_elapsed"))]
 for k in keys:
     if k in m:
         print("%-70s %s" % (k, m[k]))
