@@ -165,7 +165,7 @@ class ClockSampler:
         self.rows, self.proc, self.thread = [], None, None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "50"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
         except Exception:
@@ -361,13 +361,15 @@ def main():
         return sums
 
     with torch.no_grad():
+        # the clock sampler starts before the warm-up: nvidia-smi needs a few hundred ms before its first row, longer than
+        # a short timed region; rows are filtered by timestamp to the timed region afterwards
+        sampler = ClockSampler(local_rank) if rank == 0 else None
         for _ in range(args.warmup):
             sums = step()
         torch.cuda.synchronize()
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
-        sampler = ClockSampler(local_rank) if rank == 0 else None
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         l0 = nb._cabi.launch_count()
         t_begin = time.perf_counter()

@@ -3,7 +3,7 @@ mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/gpus.txt
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 3 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_swap12_n2.json
 timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 2 --warmup 3 --workload swarm50 --samples 65536 2>&1 | tail -1 > gpurun_out/bench_swarm50_n2.json
-timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 2>&1 | tail -1 > gpurun_out/bench_swap12_n1.json
+timeout 600 python bench.py --gpus 1 --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/bench_swap12_n1.json
 for W in softcorridor swap2 swap12 singlequad swarm50; do timeout 300 python bench.py --latency --workload $W 2>&1 | tail -1 > gpurun_out/latency_$W.json; done
 python - <<PY
 import json,glob
