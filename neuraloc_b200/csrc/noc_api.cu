@@ -455,6 +455,9 @@ int launch_tc_0(const TcArgs&, int, cudaStream_t, double*);
 int launch_tc_1(const TcArgs&, int, cudaStream_t, double*);
 int launch_tc_2(const TcArgs&, int, cudaStream_t, double*);
 int launch_tc_3(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_4(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_5(const TcArgs&, int, cudaStream_t, double*);
+int launch_tc_6(const TcArgs&, int, cudaStream_t, double*);
 static int tc_shape_id(const noc_phi_t* ph, const noc_prob_t* pb) {
     if (ph->nTh != 2 || ph->m < 1 || ph->m > 128) return -1;
     int shape = -1;
@@ -463,6 +466,9 @@ static int tc_shape_id(const noc_phi_t* ph, const noc_prob_t* pb) {
         if (pb->nAgents == 2) shape = 1;
         if (pb->nAgents == 4) shape = 2;
         if (pb->nAgents == 12) shape = 3;
+        if (pb->nAgents == 6) shape = 4;
+        if (pb->nAgents == 8) shape = 5;
+        if (pb->nAgents == 10) shape = 6;
     }
     if (shape < 0) return -1;
     const int mp = align_up(ph->m, shape == 0 ? 64 : 16), KS = align_up(ph->d + 2, 16);
@@ -493,6 +499,9 @@ static int tc_launch(int shape, int m, int r, double h, const PhiRaw<float>& raw
         case 1: rc = launch_tc_1(A, lim, st, sums); break;
         case 2: rc = launch_tc_2(A, lim, st, sums); break;
         case 3: rc = launch_tc_3(A, lim, st, sums); break;
+        case 4: rc = launch_tc_4(A, lim, st, sums); break;
+        case 5: rc = launch_tc_5(A, lim, st, sums); break;
+        case 6: rc = launch_tc_6(A, lim, st, sums); break;
         default: rc = fail(NOC_ERR_ARG, "bad tensor-core shape %d", shape);
     }
     cudaError_t e = cudaFreeAsync(dev, st);

@@ -31,8 +31,14 @@ using Shape = TcShape<0, 2, NOC_TC_CH1, NOC_TC_MINB1>;     // Cross2D, 2 agents,
 using Shape = TcShape<0, 4, 16, 3>;     // Cross2D, 4 agents, d = 8 (midcross4)
 #elif NOC_TC_SHAPE == 3
 using Shape = TcShape<0, 12, NOC_TC_CH3, NOC_TC_MINB3>;    // Cross2D, 12 agents, d = 24 (swap12)
+#elif NOC_TC_SHAPE == 4
+using Shape = TcShape<0, 6, 16, 3>;     // Cross2D, 6 agents, d = 12 (swap12_3pair)
+#elif NOC_TC_SHAPE == 5
+using Shape = TcShape<0, 8, 16, 3>;     // Cross2D, 8 agents, d = 16 (swap12_4pair)
+#elif NOC_TC_SHAPE == 6
+using Shape = TcShape<0, 10, 16, 3>;    // Cross2D, 10 agents, d = 20 (swap12_5pair)
 #else
-#error "NOC_TC_SHAPE must be 0..3"
+#error "NOC_TC_SHAPE must be 0..6"
 #endif
 
 #define NOC_TC_NAME2(k) launch_tc_##k

@@ -244,11 +244,14 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     constexpr unsigned kK0n = (2 * sboS) >> 4;           // ... of K0b read MN-major
 
     // publish my operand writes and let thread 0 issue `issue`; mma_wait() then blocks until the tensor core is done
-    auto mma_issue = [&](auto issue) {
+    // The issuing warp rotates with the GEMM (warp g issues GEMM-g): the ~25 instructions per mma6 are then spread over
+    // four warps instead of lengthening warp 0's critical path in every round.  Ordering is safe: each GEMM is issued
+    // after a block barrier that follows every thread's wait on the previous GEMM's commit.
+    auto mma_issue = [&](int who, auto issue) {
         fence_async_smem();
         tc_fence_before();
         __syncthreads();
-        if (warp_u == 0) {                               // warp-uniform branch, then one elected lane
+        if (warp_u == who) {                             // warp-uniform branch, then one elected lane
             if (elect_one_sync()) {
                 tc_fence_after();
                 issue();
@@ -262,7 +265,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         phase ^= 1;
         tc_fence_after();
     };
-    auto run_mma = [&](auto issue) { mma_issue(issue); mma_wait(); };
+    auto run_mma = [&](int who, auto issue) { mma_issue(who, issue); mma_wait(); };
 
     // calcLHQW / calcGradpH / calcCtrls in registers, in two parts (Cross2D.py:69-87,133-165; Quadcopter.py:65-113,160-197).
     // Part 1 needs only x and runs while GEMM-1 is in flight: the terrain and interaction costs (q, w) of Cross2D, or the
@@ -332,7 +335,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = (k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f)); }
             store_chunk3(sS, pS, row, c0, KS, v);
         }
-        mma_issue([&] {                                  // GEMM-1: O = S . K0b'
+        mma_issue(0, [&] {                               // GEMM-1: O = S . K0b'
 #pragma unroll
             for (int kb = 0; kb < KS / 16; ++kb) mma6(tacc, tcor, dS + kb * 16, qS, dK0k + kb * 16, qK0, idesc_m_k, kb > 0);
         });
@@ -347,7 +350,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
 #pragma unroll
             for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
         }
-        run_mma([&] {                                    // GEMM-2: A1 = U0 . K1'  (B K-major)
+        run_mma(1, [&] {                                 // GEMM-2: A1 = U0 . K1'  (B K-major)
             for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1k + kb * 16, qK1, idesc_m_k, kb > 0);
         });
         float phiN = 0.f;
@@ -358,10 +361,14 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             for (int q = 0; q < CH / 8; ++q) {
                 float u8[8];
                 if (terminal) load_chunk3(sX, pX, row, c0 + q * 8, mp, u8);      // u0, before it is overwritten
+                float b8[8], w8[8];                       // 16-byte loads of the bias and w (16-byte aligned by construction)
+                *reinterpret_cast<float4*>(b8) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8);
+                *reinterpret_cast<float4*>(b8 + 4) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8 + 4);
+                *reinterpret_cast<float4*>(w8) = *reinterpret_cast<const float4*>(sw + c0 + q * 8);
+                *reinterpret_cast<float4*>(w8 + 4) = *reinterpret_cast<const float4*>(sw + c0 + q * 8 + 4);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const int col = c0 + q * 8 + e;
-                    const float pre = v[q * 8 + e] + sb1[col], wv = sw[col];
+                    const float pre = v[q * 8 + e] + b8[e], wv = w8[e];
                     if (terminal) {
                         float av, tv;
                         act_tanh(pre, av, tv);
@@ -375,7 +382,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             }
         }
         if (SPLIT > 1 && terminal && hf > 0) sphi[(hf - 1) * 128 + row] = phiN;
-        run_mma([&] {                                    // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
+        run_mma(2, [&] {                                 // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
             for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1n + kb * kK1n, qK1, idesc_m_mn, kb > 0);
         });
         for (int c0 = cbeg; c0 < cend; c0 += CH) {            // v = tanh(o) * (w + h z1acc) -> X operand
@@ -383,11 +390,15 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
             tmem_ld<CH>(tT0 + lane_bits + c0, tt);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) v[i] = tt[i] * (sw[c0 + i] + A.h * v[i]);
+            for (int i = 0; i < CH; i += 4) {
+                const float4 w4 = *reinterpret_cast<const float4*>(sw + c0 + i);
+                v[i] = tt[i] * (w4.x + A.h * v[i]); v[i + 1] = tt[i + 1] * (w4.y + A.h * v[i + 1]);
+                v[i + 2] = tt[i + 2] * (w4.z + A.h * v[i + 2]); v[i + 3] = tt[i + 3] * (w4.w + A.h * v[i + 3]);
+            }
 #pragma unroll
             for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
         }
-        run_mma([&] {                                    // GEMM-4: G = V . K0b (MN-major view) + S . symb'
+        run_mma(3, [&] {                                 // GEMM-4: G = V . K0b (MN-major view) + S . symb'
             for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK0n + kb * kK0n, qK0, idesc_s_mn, kb > 0);
             // the terminal evaluation needs S.symb' on its own (Phi's quadratic term): it goes to the free tanh columns
             const unsigned qm = terminal ? tT0 : tacc, qc = terminal ? tTq : tcor;

@@ -53,6 +53,19 @@ def test_tc_rk1_and_unknown_stepper_golden(nb, name):
     _compare("f32", d, got, (c["nostep_mean_f32"], None, c["nostep_z_f32"], c["nostep_ctrl_f32"]), "tc no stepper")
 
 
+def test_tc_shock_restart_golden(nb):
+    """tspan != [0,1] (plotter.py:817-823) through the tensor-core kernel."""
+    c = load_cases("softcorridor")
+    net, prob, xinit, meta = product_setup("softcorridor", DT["f32"])
+    nt = int(c["nt"])
+    nS = int(0.1 * nt)
+    got = _three_modes(nb, xinit, net, prob, [0.0, 0.1], nS, "rk4", meta["alph"])
+    _compare("f32", 4, got, (c["shock1_mean_f32"], None, c["shock1_z_f32"], c["shock1_ctrl_f32"]), "tc shock leg 1")
+    xs = torch.from_numpy(c["shock2_x_f32"]).float().cuda()
+    got = _three_modes(nb, xs, net, prob, [0.1, 1.0], 1 + nt - nS, "rk4", meta["alph"])
+    _compare("f32", 4, got, (c["shock2_mean_f32"], None, c["shock2_z_f32"], c["shock2_ctrl_f32"]), "tc shock leg 2")
+
+
 def _vs_tile(nb, monkeypatch, net, prob, x, alph, nt, d, full):
     with torch.no_grad():
         Jt, ct = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", alph, noMean=True)
@@ -90,7 +103,7 @@ def test_tc_matches_fma_tile_kernel(nb, name, n, monkeypatch):
 
 
 @pytest.mark.parametrize("m", [8, 20, 48, 100, 128])
-@pytest.mark.parametrize("data", ["midcross4", "swap2", "swap12", "singlequad"])
+@pytest.mark.parametrize("data", ["midcross4", "swap2", "swap12", "singlequad", "swap12_3pair", "swap12_4pair", "swap12_5pair"])
 def test_tc_random_nets_any_width(nb, data, m, monkeypatch):
     """Randomly initialised value nets of widths that are not multiples of the MMA tile (zero-padded units), the 4-agent
     shape and the hard obstacle, train and eval mode of the problem."""
