@@ -124,9 +124,10 @@ __device__ __forceinline__ void tmem_st32_bits(unsigned taddr, const unsigned (&
                     "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, int ncols) {      // one warp; writes the base address to smem
+// one warp; writes the base address to smem.  `last` = no further allocation by this CTA (gives up the permit)
+__device__ __forceinline__ void tmem_alloc(unsigned smem_dst, int ncols, bool last = true) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (last) asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void tmem_dealloc(unsigned taddr, int ncols) {       // the same warp that allocated
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");

@@ -54,6 +54,7 @@ struct TcArgs {
     double* partials;
     float* out_a; float* out_b; float* out_c;
     int ntiles, tmem_cols;
+    int park_col;                   // PARK shapes: column of the parked RK accumulator inside the main block, or -1 = own 32-column block
 };
 
 // problem shapes the kernel is instantiated for
@@ -68,6 +69,9 @@ struct TcShape {
     static constexpr int MINB = MINB_;
     static constexpr int SPLIT = SPLIT_;                           // threads per sample: each owns 1/SPLIT of the hidden units in the epilogues
     static constexpr int NT = 128 * SPLIT;
+    // wide states: the RK accumulator is parked in 32 extra TMEM columns during each evaluation instead of being
+    // spilled to local memory by the compiler (L1 is tiny next to ~200 KB of shared memory: every spill was an L2 trip)
+    static constexpr bool PARK = (NZ > 20) && (NZ <= 32) && SPLIT == 1;
     static_assert(KIND != 2 || NA == 1, "one quadcopter");
 };
 
@@ -183,7 +187,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     float* sred = scw + KS;                              // 4 warps x 8
     float* sphi = sred + 32;                             // (SPLIT - 1) x 128: partial w.u1 of the other threads of a sample
     __shared__ __align__(8) unsigned long long mbar;
-    __shared__ unsigned tmem_base_s;
+    __shared__ unsigned tmem_base_s, tmem_park_s;
 
     // ---- one-time per CTA: weights -> split bf16 operands in canonical layout (padded units have zero weights: they
     //      contribute exactly nothing to any contraction)
@@ -216,7 +220,11 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     }
     for (int i = tid; i < mp; i += NT) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] : 0.f; }
     if (tid < KS) scw[tid] = (tid < D) ? A.c_w[tid] : 0.f;
-    if (warp == 0) tmem_alloc(smem_u32(&tmem_base_s), A.tmem_cols);
+    if (warp == 0) {
+        const bool own = SH::PARK && A.park_col < 0;
+        tmem_alloc(smem_u32(&tmem_base_s), A.tmem_cols, !own);
+        if (own) tmem_alloc(smem_u32(&tmem_park_s), 32, true);
+    }
     if (tid == 0) mbar_init(smem_u32(&mbar), 1);
     fence_async_smem();
     tc_fence_before();
@@ -224,6 +232,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     tc_fence_after();
     const int C = (mp > KS) ? mp : KS;
     const unsigned tacc = tmem_base_s;                   // hi*hi accumulator, columns [0, C)
+    const unsigned tpark = !SH::PARK ? 0u : (A.park_col < 0 ? tmem_park_s : tacc + (unsigned)A.park_col);
     const unsigned tcor = tacc + C;                      // correction-term accumulator, same column map
     const unsigned tT0 = tacc + 2 * C;                   // tanh(o); at the terminal evaluation also S.symb' (main)
     const unsigned tTq = tacc + 3 * C;                   // terminal evaluation only: S.symb' (corrections), KS columns
@@ -474,7 +483,11 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         const bool valid = row < nvalid;
         const bool writer = valid && hf == 0;                          // one thread per sample writes results
         const long long gs = s0 + (valid ? row : nvalid - 1);        // padding threads replay the last valid sample
-        float z0[NZ], za[NZ];
+        float z0[NZ], za[SH::PARK ? 32 : NZ];
+        if (SH::PARK) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) za[c] = 0.f;
+        }
 #pragma unroll
         for (int c = 0; c < d; ++c) z0[c] = A.x[gs * d + c];
 #pragma unroll
@@ -498,7 +511,9 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             const int k = ei.x, kind = ei.y, first = ei.z, last = ei.w;
             const bool term = (kind == 2);
             float xq[3];
+            if (SH::PARK) tmem_st<32>(tpark + lane_bits, za);
             chain(xs, tcur, g, term, phi1, xq);
+            if (SH::PARK) tmem_ld<32>(tpark + lane_bits, za);
             if (term) break;
             float rate[4], uc;
             problem(xs, g, xq, dx, rate, uc);
@@ -574,7 +589,10 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tacc, A.tmem_cols);
+    if (warp == 0) {
+        tmem_dealloc(tacc, A.tmem_cols);
+        if (SH::PARK && A.park_col < 0) tmem_dealloc(tpark, 32);
+    }
 }
 
 // host: the flat evaluation sequence of one rollout from the stage-time table (nt x 5 doubles, noc_stage_times)
@@ -624,9 +642,12 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     A.tmem_cols = tc_tmem_cols(A.mp, SH::KS);
     const int by_regs = regs_sm / (align_up(std::max(fa.numRegs, 1), 8) * SH::NT);
     const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
-    int per_sm = std::min(std::min(by_regs, by_smem), 512 / A.tmem_cols);
+    const int tmem_used = 3 * std::max(A.mp, SH::KS) + SH::KS;
+    A.park_col = (SH::PARK && A.tmem_cols - tmem_used >= 32) ? tmem_used : -1;      // spare columns of the power-of-two block
+    const int tmem_per_cta = A.tmem_cols + ((SH::PARK && A.park_col < 0) ? 32 : 0);
+    int per_sm = std::min(std::min(by_regs, by_smem), 512 / tmem_per_cta);
     if (getenv("NOC_DEBUG"))
-        fprintf(stderr, "[noc] tc occupancy: api=%d regs=%d (->%d) smem->%d tmem->%d\n", occ_api, fa.numRegs, by_regs, by_smem, 512 / A.tmem_cols);
+        fprintf(stderr, "[noc] tc occupancy: api=%d regs=%d (->%d) smem->%d tmem->%d\n", occ_api, fa.numRegs, by_regs, by_smem, 512 / tmem_per_cta);
     if (per_sm < 1) return fail(NOC_ERR_NOMEM, "tensor-core rollout does not fit on an SM");
     A.ntiles = (int)((A.n + 127) / 128);
     const int grid = std::max(1, std::min(A.ntiles, per_sm * sm_count()));
