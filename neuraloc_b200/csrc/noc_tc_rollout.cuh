@@ -71,7 +71,8 @@ struct TcShape {
     static constexpr int NT = 128 * SPLIT;
     // wide states: the RK accumulator is parked in 32 extra TMEM columns during each evaluation instead of being
     // spilled to local memory by the compiler (L1 is tiny next to ~200 KB of shared memory: every spill was an L2 trip)
-    static constexpr bool PARK = (NZ > 20) && (NZ <= 32) && SPLIT == 1;
+    static constexpr bool PARK = ((NZ > 20) && (NZ <= 32) && SPLIT == 1) || (KIND == 2);
+    static constexpr int PW = (NZ <= 16) ? 16 : 32;                 // parked columns per thread
     static_assert(KIND != 2 || NA == 1, "one quadcopter");
 };
 
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     if (warp == 0) {
         const bool own = SH::PARK && A.park_col < 0;
         tmem_alloc(smem_u32(&tmem_base_s), A.tmem_cols, !own);
-        if (own) tmem_alloc(smem_u32(&tmem_park_s), 32, true);
+        if (own) tmem_alloc(smem_u32(&tmem_park_s), 32, true);        // (own block only for SPLIT == 1, PW == 32 shapes)
     }
     if (tid == 0) mbar_init(smem_u32(&mbar), 1);
     fence_async_smem();
@@ -232,7 +233,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     tc_fence_after();
     const int C = (mp > KS) ? mp : KS;
     const unsigned tacc = tmem_base_s;                   // hi*hi accumulator, columns [0, C)
-    const unsigned tpark = !SH::PARK ? 0u : (A.park_col < 0 ? tmem_park_s : tacc + (unsigned)A.park_col);
+    const unsigned tpark = !SH::PARK ? 0u : (A.park_col < 0 ? tmem_park_s : tacc + (unsigned)A.park_col) + (unsigned)(hf * SH::PW);
     const unsigned tcor = tacc + C;                      // correction-term accumulator, same column map
     const unsigned tT0 = tacc + 2 * C;                   // tanh(o); at the terminal evaluation also S.symb' (main)
     const unsigned tTq = tacc + 3 * C;                   // terminal evaluation only: S.symb' (corrections), KS columns
@@ -483,10 +484,10 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         const bool valid = row < nvalid;
         const bool writer = valid && hf == 0;                          // one thread per sample writes results
         const long long gs = s0 + (valid ? row : nvalid - 1);        // padding threads replay the last valid sample
-        float z0[NZ], za[SH::PARK ? 32 : NZ];
+        float z0[NZ], za[SH::PARK ? SH::PW : NZ];
         if (SH::PARK) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) za[c] = 0.f;
+            for (int c = 0; c < SH::PW; ++c) za[c] = 0.f;
         }
 #pragma unroll
         for (int c = 0; c < d; ++c) z0[c] = A.x[gs * d + c];
@@ -511,9 +512,9 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             const int k = ei.x, kind = ei.y, first = ei.z, last = ei.w;
             const bool term = (kind == 2);
             float xq[3];
-            if (SH::PARK) tmem_st<32>(tpark + lane_bits, za);
+            if (SH::PARK) tmem_st<SH::PW>(tpark + lane_bits, za);
             chain(xs, tcur, g, term, phi1, xq);
-            if (SH::PARK) tmem_ld<32>(tpark + lane_bits, za);
+            if (SH::PARK) tmem_ld<SH::PW>(tpark + lane_bits, za);
             if (term) break;
             float rate[4], uc;
             problem(xs, g, xq, dx, rate, uc);
@@ -639,11 +640,22 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     NOC_CUDA(cudaGetDevice(&dev));
     NOC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
     NOC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
+    // TMEM columns: main | corr | tanh(o) | terminal-only S.symb corr, in one power-of-two block; PARK shapes add the parked
+    // RK accumulator: in the block's spare columns when there are any, else (one thread per sample, 32 columns) in a second
+    // 32-column block so that e.g. swap12 stays at 160 columns = 3 CTAs per SM, else by growing the block
+    const int tmem_used = 3 * std::max(A.mp, SH::KS) + SH::KS, park_need = SH::PW * SH::SPLIT;
     A.tmem_cols = tc_tmem_cols(A.mp, SH::KS);
+    A.park_col = -1;
+    if (SH::PARK) {
+        if (A.tmem_cols - tmem_used >= park_need) A.park_col = tmem_used;
+        else if (park_need != 32) {
+            while (A.tmem_cols - tmem_used < park_need) A.tmem_cols *= 2;
+            if (A.tmem_cols > 512) return fail(NOC_ERR_NOMEM, "no TMEM columns left for the parked state");
+            A.park_col = tmem_used;
+        }
+    }
     const int by_regs = regs_sm / (align_up(std::max(fa.numRegs, 1), 8) * SH::NT);
     const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
-    const int tmem_used = 3 * std::max(A.mp, SH::KS) + SH::KS;
-    A.park_col = (SH::PARK && A.tmem_cols - tmem_used >= 32) ? tmem_used : -1;      // spare columns of the power-of-two block
     const int tmem_per_cta = A.tmem_cols + ((SH::PARK && A.park_col < 0) ? 32 : 0);
     int per_sm = std::min(std::min(by_regs, by_smem), 512 / tmem_per_cta);
     if (getenv("NOC_DEBUG"))
