@@ -280,6 +280,11 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     // calcLHQW / calcGradpH / calcCtrls in registers, in two parts (Cross2D.py:69-87,133-165; Quadcopter.py:65-113,160-197).
     // Part 1 needs only x and runs while GEMM-1 is in flight: the terrain and interaction costs (q, w) of Cross2D, or the
     // thrust direction (f7, f8, f9) of the quadcopter, returned in xq[0..3).
+    // the problem's python-double parameters, rounded to fp32 once (the reference rounds them to the tensor dtype at use);
+    // left as doubles inside the loop they cost FP64-pipe compares / converts in every evaluation
+    const bool hasQ = (pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0), hasW = (pr.alph_W != 0.0), posQ = (pr.alph_Q > 0.0);
+    const float f_alphQ = float(pr.alph_Q), f_alphW = float(pr.alph_W), f_cut = float(pr.cutW), f_c2 = float(2 * pr.r * pr.r);
+    const float f_mass = float(pr.mass), f_grav = float(pr.grav), f_uscale = float(-1.0 / (2.0 * pr.mass));
     auto problem_x = [&](const float (&x)[d], float (&xq)[3]) {
         if constexpr (KIND == 2) {
             float sps, cps, sth, cth, sph, cph;
@@ -288,12 +293,12 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         } else {
             constexpr int NA = SH::NA, DIM = SH::DIM;
             float q = 0.f, w = 0.f;
-            if ((pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0)) {
+            if (hasQ) {
 #pragma unroll
                 for (int a = 0; a < NA; ++a) q += terrain_agent<float>(pr, x[a * DIM], x[a * DIM + 1], DIM == 3 ? x[a * DIM + DIM - 1] : 0.f);
             }
-            if (pr.alph_W != 0.0 && NA >= 2) {
-                const float cut = float(pr.cutW), c2 = float(2 * pr.r * pr.r);
+            if (hasW && NA >= 2) {
+                const float cut = f_cut, c2 = f_c2;
                 if constexpr (NA == 2) {               // Cross2D.py:133-145: no "== 1" rule here
                     float d2 = 0.f;
 #pragma unroll
@@ -442,18 +447,18 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         if constexpr (KIND == 2) {
             const float f7 = xq[0], f8 = xq[1], f9 = xq[2];
             const float fp = f7 * g[6] + f8 * g[7] + f9 * g[8];
-            const float u = float(-1.0 / (2.0 * pr.mass)) * fp;
+            const float u = f_uscale * fp;
             const float sq = g[9] * g[9] + g[10] * g[10] + g[11] * g[11];
-            float L = float(pr.alph_Q) * 0.f;
+            float L = f_alphQ * 0.f;
             L = L + 2.f + u * u + 0.25f * sq;
-            const float um = u / float(pr.mass);
+            const float um = u / f_mass;
             const float xv = x[6] * g[0] + x[7] * g[1] + x[8] * g[2];
             const float xw = x[9] * g[3] + x[10] * g[4] + x[11] * g[5];
-            const float H = 0.f - L - xv - xw - um * fp + float(pr.grav) * g[8] + 0.5f * sq;
+            const float H = 0.f - L - xv - xw - um * fp + f_grav * g[8] + 0.5f * sq;
             rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = 0.f; rate[3] = 0.f;
 #pragma unroll
             for (int c = 0; c < 6; ++c) dx[c] = x[6 + c];
-            dx[6] = -(-um * f7); dx[7] = -(-um * f8); dx[8] = -(-um * f9 + float(pr.grav));
+            dx[6] = -(-um * f7); dx[7] = -(-um * f8); dx[8] = -(-um * f9 + f_grav);
 #pragma unroll
             for (int c = 9; c < 12; ++c) dx[c] = -(0.5f * g[c]);
             uctrl = u;
@@ -463,9 +468,9 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
 #pragma unroll
             for (int r = 0; r < d; ++r) pp = fmaf(g[r], g[r], pp);
             float Qret, L;
-            if (pr.kind == 0) { Qret = float(pr.alph_Q) * q; L = 0.5f * pp + Qret; }     // Cross2D returns Q pre-scaled (quirk 6)
-            else { Qret = (pr.alph_Q > 0.0) ? q : 0.f; L = 0.5f * pp + float(pr.alph_Q) * Qret; }
-            if (pr.alph_W != 0.0) L = L + float(pr.alph_W) * w; else w = 0.f;
+            if (pr.kind == 0) { Qret = f_alphQ * q; L = 0.5f * pp + Qret; }     // Cross2D returns Q pre-scaled (quirk 6)
+            else { Qret = posQ ? q : 0.f; L = 0.5f * pp + f_alphQ * Qret; }
+            if (hasW) L = L + f_alphW * w; else w = 0.f;
             const float H = -L + pp;
             rate[0] = L; rate[1] = fabsf(g[d] - H); rate[2] = Qret; rate[3] = w;
 #pragma unroll
