@@ -1,9 +1,11 @@
 // noc_tc_rollout.cuh — tensor-core (tcgen05 / TMEM) rollout kernel, fp32 in / fp32 out, for value networks with
 // nTh = 2 and m <= 128 on problems whose state fits one thread's registers (d <= 24).
 //
-// One CTA of 128 threads owns a tile of 128 samples; THREAD r IS SAMPLE r: it keeps the augmented state z = [x, L, HJt, Q, W]
-// and the RK accumulator in registers for all nt steps, evaluates the problem terms (calcLHQW / calcGradpH / calcCtrls)
-// in registers, and is the epilogue thread of TMEM lane r.  The four contractions of one grad-Phi evaluation
+// One CTA owns a tile of 128 samples; THREAD r IS SAMPLE r (SPLIT > 1: SPLIT threads per sample, each owning 1/SPLIT of the
+// hidden units in the epilogues and all of them keeping the per-sample state): it keeps the augmented state
+// z = [x, L, HJt, Q, W] and the RK accumulator in registers for all nt steps (the accumulator parked in spare TMEM columns
+// during an evaluation for wide states), evaluates the problem terms (calcLHQW / calcGradpH / calcCtrls) in registers, and is
+// an epilogue thread of TMEM lane r.  The four contractions of one grad-Phi evaluation
 // (Phi.py:99-138) run on the 5th-generation tensor cores with M = 128 samples:
 //     GEMM-1  O  [128 x m]  = S [128 x KS] . K0b'     S = [x, t, 1, 0..]  (the 1-column folds the bias b0 in)
 //     GEMM-2  A1 [128 x m]  = U0 [128 x m] . K1'      B = K1 read K-major
@@ -19,7 +21,7 @@
 // fp32 FMA kernels and as torch's own fp32 (scripts/accuracy_probe.py).
 //
 // Operands are written by the epilogue threads straight into the canonical no-swizzle UMMA layout (8-row x 16-byte core
-// matrices), one thread issues the MMAs, and tcgen05.commit signals an mbarrier the 128 epilogue threads wait on.
+// matrices), one elected lane issues the MMAs, and tcgen05.commit signals an mbarrier all epilogue threads wait on.
 // Several CTAs share an SM when shared memory and TMEM columns allow, so one tile's epilogue overlaps another's MMAs.
 #pragma once
 #include "noc_launch.cuh"
