@@ -55,6 +55,7 @@ struct TcArgs {
     float alph0, alph3, alph4, alph5, t_end;
     double* partials;
     float* out_a; float* out_b; float* out_c;
+    float* stage;                   // intermediates: tile-major staging buffer [tile][step][row][128 samples] (coalesced), or NULL
     int ntiles, tmem_cols;
     int park_col;                   // PARK shapes: column of the parked RK accumulator inside the main block, or -1 = own 32-column block
 };
@@ -166,7 +167,8 @@ static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) |
     return c;
 }
 
-template <class SH>
+// INTER: the intermediates=True build (trajectory + control outputs); the mean / noMean build carries none of that code
+template <class SH, bool INTER>
 __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcArgs A) {
     constexpr int d = SH::d, D = SH::D, KS = SH::KS, NZ = SH::NZ, NCTRL = SH::NCTRL, CH = SH::CH, KIND = SH::KIND;
     constexpr int SPLIT = SH::SPLIT, NT = SH::NT;
@@ -483,7 +485,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
 
     double csum[7] = {0, 0, 0, 0, 0, 0, 0};
     long long cnt = 0;
-    const bool inter = (A.mode == 2);
+    constexpr bool inter = INTER;
     const int ntp1 = A.nt + 1;
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const long long s0 = (long long)tile * 128;
@@ -500,11 +502,23 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         for (int c = 0; c < d; ++c) z0[c] = A.x[gs * d + c];
 #pragma unroll
         for (int c = d; c < NZ; ++c) z0[c] = 0.f;
+        // intermediates: trajectory column `col` of (row c of zFull | row c of ctrlFull).  With a staging buffer the warp
+        // writes 128 contiguous bytes per (step, row) and tc_untile_kernel transposes into the reference layout
+        // [n, rows, nt+1] afterwards; without one (allocation failed) each thread writes its strided 4-byte element.
+        // (addresses are recomputed at each use: nothing of this stays live in the mean / noMean modes)
+        auto put_z = [&](int c, int col, float v) {
+            if (A.stage) A.stage[(((size_t)tile * ntp1 + col) * (NZ + NCTRL) + c) * 128 + row] = v;
+            else A.out_b[(gs * NZ + c) * ntp1 + col] = v;
+        };
+        auto put_u = [&](int c, int col, float v) {
+            if (A.stage) A.stage[(((size_t)tile * ntp1 + col) * (NZ + NCTRL) + NZ + c) * 128 + row] = v;
+            else A.out_c[(gs * NCTRL + c) * ntp1 + col] = v;
+        };
         if (inter && writer) {                                         // zFull[:,:,0] = z, ctrlFull[:,:,0] = 0 (OCflow.py:37-43)
 #pragma unroll
-            for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1] = z0[c];
+            for (int c = 0; c < NZ; ++c) put_z(c, 0, z0[c]);
 #pragma unroll
-            for (int c = 0; c < NCTRL; ++c) A.out_c[(gs * NCTRL + c) * ntp1] = 0.f;
+            for (int c = 0; c < NCTRL; ++c) put_u(c, 0, 0.f);
         }
         // ONE call site for the chain: the evaluations of a rollout are a flat host-built sequence (TcEval); `xs` always
         // holds the next evaluation's input.
@@ -525,17 +539,17 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             if (term) break;
             float rate[4], uc;
             problem(xs, g, xq, dx, rate, uc);
-            if (kind == 1) {                                         // controls at the new state, OLD time (quirk 3)
+            if (INTER && kind == 1) {                                // controls at the new state, OLD time (quirk 3)
                 if (writer) {
 #pragma unroll
-                    for (int c = 0; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1 + (k + 1)] = z0[c];
+                    for (int c = 0; c < NZ; ++c) put_z(c, k + 1, z0[c]);
                     if constexpr (KIND == 2) {
-                        A.out_c[(gs * 4 + 0) * ntp1 + (k + 1)] = uc;
+                        put_u(0, k + 1, uc);
 #pragma unroll
-                        for (int c = 1; c < 4; ++c) A.out_c[(gs * 4 + c) * ntp1 + (k + 1)] = -0.5f * g[8 + c];
+                        for (int c = 1; c < 4; ++c) put_u(c, k + 1, -0.5f * g[8 + c]);
                     } else {
 #pragma unroll
-                        for (int c = 0; c < d; ++c) A.out_c[(gs * d + c) * ntp1 + (k + 1)] = -g[c];
+                        for (int c = 0; c < d; ++c) put_u(c, k + 1, -g[c]);
                     }
                 }
                 continue;
@@ -631,10 +645,32 @@ static inline void tc_build_evals(const double* tab, int nt, int stepper, bool i
     ev.push_back(e);
 }
 
+// staging buffer [tile][step][row][128] -> zFull [n, NZ, ntp1] and ctrlFull [n, NCTRL, ntp1] (last dim contiguous).
+// One block per (tile, row): coalesced 512-byte reads, a padded shared-memory transpose, (nt+1)-float contiguous writes.
+constexpr int kUntileSteps = 64;
+static __global__ void __launch_bounds__(128) tc_untile_kernel(const float* __restrict__ stage, float* __restrict__ zFull,
+                                                               float* __restrict__ ctrlFull, long long n, int ntp1, int NZ, int NCTRL) {
+    __shared__ float tl[kUntileSteps * 129];
+    const int t = blockIdx.x, r = blockIdx.y, R = NZ + NCTRL, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long s0 = (long long)t * 128;
+    const int nvalid = (int)((n - s0 < 128) ? (n - s0) : 128);
+    float* out = (r < NZ) ? zFull : ctrlFull;
+    const int rr = (r < NZ) ? r : r - NZ, RR = (r < NZ) ? NZ : NCTRL;
+    for (int k0 = 0; k0 < ntp1; k0 += kUntileSteps) {
+        const int kc = (ntp1 - k0 < kUntileSteps) ? (ntp1 - k0) : kUntileSteps;
+        if ((int)threadIdx.x < nvalid)
+            for (int k = 0; k < kc; ++k) tl[k * 129 + threadIdx.x] = stage[(((size_t)t * ntp1 + k0 + k) * R + r) * 128 + threadIdx.x];
+        __syncthreads();
+        for (int l = warp; l < nvalid; l += 4)
+            for (int k = lane; k < kc; k += 32) out[((s0 + l) * RR + rr) * ntp1 + k0 + k] = tl[k * 129 + l];
+        __syncthreads();
+    }
+}
+
 template <class SH>
 int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     const size_t smem = tc_smem_bytes(A.mp, SH::KS);
-    auto kern = rollout_tc_kernel<SH>;
+    auto kern = (A.mode == NOC_MODE_INTERMEDIATES) ? rollout_tc_kernel<SH, true> : rollout_tc_kernel<SH, false>;
     if (smem + 1024 > (size_t)smem_limit) return fail(NOC_ERR_NOMEM, "tensor-core rollout needs %zu B of shared memory", smem);
     NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // resident CTAs per SM from the kernel's own resource use (registers, shared memory incl. the 1 KB the driver reserves
@@ -678,9 +714,23 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
         NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)grid, st));
         A.partials = partials;
     }
+    // intermediates: stage the trajectories tile-major (coalesced) and transpose afterwards; if the staging buffer (as large
+    // as the outputs) cannot be allocated the kernel writes the reference layout directly (strided, slower, same result)
+    float* stage = nullptr;
+    if (A.mode == NOC_MODE_INTERMEDIATES) {
+        const size_t bytes = sizeof(float) * (size_t)A.ntiles * (A.nt + 1) * (SH::NZ + SH::NCTRL) * 128;
+        if (cudaMallocAsync((void**)&stage, bytes, st) != cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
+    }
+    A.stage = stage;
     kern<<<grid, SH::NT, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
+    if (stage) {
+        tc_untile_kernel<<<dim3(A.ntiles, SH::NZ + SH::NCTRL), 128, 0, st>>>(stage, A.out_b, A.out_c, A.n, A.nt + 1, SH::NZ, SH::NCTRL);
+        count_launch();
+        NOC_CUDA(cudaGetLastError());
+        NOC_CUDA(cudaFreeAsync(stage, st));
+    }
     if (partials) {
         int frc = launch_finish(partials, grid, out_sums, st);
         if (frc) return frc;
