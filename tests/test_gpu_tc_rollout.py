@@ -126,6 +126,38 @@ def test_tc_random_nets_any_width(nb, data, m, monkeypatch):
         _vs_tile(nb, monkeypatch, net, prob, x.cuda(), alph, 6, d, True)
 
 
+@pytest.mark.parametrize("name,n", [("swap12", 70_000), ("singlequad", 25_000)])
+def test_tc_several_tiles_per_cta(nb, name, n, monkeypatch):
+    """More tiles than resident CTAs (444 x 128 samples for swap12, 148 x 128 for singlequad), ragged last tile: every CTA
+    loops over tiles; intermediates go through the tile-major staging buffer and the transpose kernel.  Trajectories,
+    controls and per-sample costs agree with the FMA tile kernel on rows from the first, a middle and the last tile."""
+    net, prob, xinit, meta = product_setup(name, torch.float32)
+    d = xinit.shape[1]
+    g = torch.Generator(device="cuda").manual_seed(n)
+    x = xinit + 0.3 * torch.randn(n, d, generator=g, device="cuda")
+    if name == "singlequad":
+        x[:, 3:] *= 0.1
+    nt = 20        # (a handful of RK4 steps over [0,1] is ill-conditioned in fp32: the two kernels' rounding noise is amplified)
+    idx = torch.tensor([0, 1, 127, 128, n // 2, n // 2 + 77, n - 130, n - 2, n - 1], device="cuda")
+    with torch.no_grad():
+        zt, ut = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        assert nb._cabi.last_path() == "tensor"
+        Jt, ct = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+        mt = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"]))
+        monkeypatch.setenv("NOC_FORCE_PATH", "tile")
+        zf, uf = nb.OCflow(x[idx].contiguous(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        Jf, cf = nb.OCflow(x[idx].contiguous(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+    assert zt.shape == (n, d + 4, nt + 1) and not ut[:, :, 0].any()
+    assert rel_state_err(zt[idx].cpu().numpy(), zf.cpu().numpy(), d) <= 5e-6
+    assert (ut[idx] - uf).abs().max() <= 1e-4 * max(1.0, float(uf.abs().max()))
+    tt = torch.cat([Jt] + list(ct), 1).double()
+    tf = torch.cat([Jf] + list(cf), 1).double()
+    sc = torch.clamp(tf.abs().max(dim=0, keepdim=True).values, min=1.0)
+    assert float(((tt[idx] - tf).abs() / sc).max()) <= 1e-4
+    assert torch.allclose(zt[:, d, -1:], ct[0], rtol=1e-6, atol=1e-6)            # accumulated L column == noMean L
+    check_costs(mt, tt.mean(dim=0).cpu().numpy(), 1e-6, 1e-7, "mean vs mean of noMean across many tiles")
+
+
 def test_path_selection(nb, monkeypatch):
     """Default choice by shape and batch size (noc_last_path): tensor-core kernel for the shapes it is written for at
     batch sizes above the small-batch threshold, NOC_TC=0 keeps the FMA tile kernel, other shapes are unaffected, and
