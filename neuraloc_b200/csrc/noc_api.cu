@@ -606,16 +606,69 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
     size_t ob = (mode == NOC_MODE_MEAN) ? sizeof(double) * 8 : (mode == NOC_MODE_NOMEAN ? sizeof(real) * (size_t)n * 8 : 0);
     size_t zb = (mode == NOC_MODE_INTERMEDIATES) ? sizeof(real) * (size_t)n * (d + 4) * (nt + 1) : 0;
     size_t cb = (mode == NOC_MODE_INTERMEDIATES) ? sizeof(real) * (size_t)n * nctrl * (nt + 1) : 0;
+    // Large mean / noMean batches are cut into chunks (multiples of 128 rows, so that the tiling and hence every per-sample
+    // result is unchanged): chunk c+1's host->device copy runs on a second stream while chunk c's rollout runs on `st`.
+    // Mean mode: one 8-double partial sum per chunk, added on the host in chunk order.  NOC_HOST_CHUNKS overrides the count.
+    int nchunk = 1;
+    if (mode != NOC_MODE_INTERMEDIATES) {
+        nchunk = (int)std::min<long long>(8, std::max<long long>(1, n / 131072));      // >= 128 Ki rows per chunk, at most 8
+        if (const char* e = getenv("NOC_HOST_CHUNKS")) nchunk = std::max(1, atoi(e));
+        const long long max_chunks = (n + 127) / 128;
+        if (nchunk > max_chunks) nchunk = (int)max_chunks;
+        if (nchunk > 64) nchunk = 64;
+    }
+    const long long rows_per = (((n + nchunk - 1) / nchunk + 127) / 128) * 128;
+    if (mode == NOC_MODE_MEAN) ob = sizeof(double) * 8 * (size_t)nchunk;
     void *xd = nullptr, *od = nullptr, *zd = nullptr, *cd = nullptr;
     NOC_CUDA(cudaMallocAsync(&xd, xb, st));
     if (ob) NOC_CUDA(cudaMallocAsync(&od, ob, st));
     if (zb) NOC_CUDA(cudaMallocAsync(&zd, zb, st));
     if (cb) NOC_CUDA(cudaMallocAsync(&cd, cb, st));
-    NOC_CUDA(cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, st));
-    int rc = ocflow_impl<real>(ph, pb, xd, n, stage_times, t0, t1, nt, stepper, alph, mode, od, zd, cd, st, dtype);
+    int rc = NOC_OK;
+    double sums_h[64 * 8];
+    if (nchunk == 1) {
+        NOC_CUDA(cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, st));
+        rc = ocflow_impl<real>(ph, pb, xd, n, stage_times, t0, t1, nt, stepper, alph, mode, od, zd, cd, st, dtype);
+    } else {
+        // streams: `cs` copies; chunks alternate between `st` and `as` so that a chunk's last, partly filled wave of tiles
+        // overlaps the next chunk's first wave instead of idling SMs
+        cudaStream_t cs = nullptr, as = nullptr;
+        cudaEvent_t ready = nullptr, joined = nullptr, copied[64] = {nullptr};
+        cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&as, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&joined, cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventRecord(ready, st);                 // xd / od exist (stream-ordered allocation on st)
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(cs, ready, 0);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(as, ready, 0);
+        for (int c = 0; c < nchunk && e == cudaSuccess && rc == NOC_OK; ++c) {
+            const long long r0 = (long long)c * rows_per, nr = std::min<long long>(rows_per, n - r0);
+            if (nr <= 0) { nchunk = c; break; }
+            const char* src = (const char*)xh + sizeof(real) * (size_t)r0 * d;
+            char* dst = (char*)xd + sizeof(real) * (size_t)r0 * d;
+            e = cudaMemcpyAsync(dst, src, sizeof(real) * (size_t)nr * d, cudaMemcpyHostToDevice, cs);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&copied[c], cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(copied[c], cs);
+            cudaStream_t ks = (c & 1) ? as : st;
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(ks, copied[c], 0);
+            if (e != cudaSuccess) break;
+            void* oc = (mode == NOC_MODE_MEAN) ? (void*)((double*)od + 8 * c) : (void*)((real*)od + 8 * (size_t)r0);
+            rc = ocflow_impl<real>(ph, pb, dst, nr, stage_times, t0, t1, nt, stepper, alph, mode, oc, nullptr, nullptr, ks, dtype);
+        }
+        if (e == cudaSuccess && as) e = cudaEventRecord(joined, as);          // st continues after the odd chunks too
+        if (e == cudaSuccess && as) e = cudaStreamWaitEvent(st, joined, 0);
+        if (e != cudaSuccess && rc == NOC_OK) rc = fail(NOC_ERR_CUDA, "chunked host rollout failed: %s", cudaGetErrorString(e));
+        if (cs) cudaStreamSynchronize(cs);
+        if (as) cudaStreamSynchronize(as);
+        for (int c = 0; c < 64; ++c) if (copied[c]) cudaEventDestroy(copied[c]);
+        if (ready) cudaEventDestroy(ready);
+        if (joined) cudaEventDestroy(joined);
+        if (cs) cudaStreamDestroy(cs);
+        if (as) cudaStreamDestroy(as);
+    }
     if (rc == NOC_OK) {
         cudaError_t e = cudaSuccess;
-        if (ob && out_h) e = cudaMemcpyAsync(out_h, od, ob, cudaMemcpyDeviceToHost, st);
+        if (ob && out_h) e = cudaMemcpyAsync((mode == NOC_MODE_MEAN) ? (void*)sums_h : out_h, od, ob, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && zb && z_h) e = cudaMemcpyAsync(z_h, zd, zb, cudaMemcpyDeviceToHost, st);
         if (e == cudaSuccess && cb && c_h) e = cudaMemcpyAsync(c_h, cd, cb, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
@@ -626,6 +679,10 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
     if (cd) cudaFreeAsync(cd, st);
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == NOC_OK && e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "rollout failed: %s", cudaGetErrorString(e));
+    if (rc == NOC_OK && mode == NOC_MODE_MEAN && out_h) {          // chunk partials -> [sums, count], fixed order
+        double* o = (double*)out_h;
+        for (int q = 0; q < 8; ++q) { double a = 0.0; for (int c = 0; c < nchunk; ++c) a += sums_h[8 * c + q]; o[q] = a; }
+    }
     return rc;
 }
 

@@ -274,6 +274,26 @@ def test_cpu_tensors_take_the_host_entry_point(nb):
     assert "{:e}".format(Jc) and float(cs[0].item()) > 0          # the drivers format with {:e} and .item()
 
 
+@pytest.mark.parametrize("chunks", ["1", "3", "7"])
+def test_host_entry_chunked_pipeline(nb, chunks, monkeypatch):
+    """noc_ocflow_host cuts large mean / noMean batches into row chunks whose host->device copies overlap the previous chunk's
+    rollout (NOC_HOST_CHUNKS forces it on a small batch): per-sample results identical to the device entry point, sums
+    equal up to the order of the double additions."""
+    monkeypatch.setenv("NOC_HOST_CHUNKS", chunks)
+    net, prob, xinit, meta = product_setup("swap12", torch.float32, device="cpu")
+    g = torch.Generator().manual_seed(3)
+    x = xinit + 0.3 * torch.randn(1000, 24, generator=g)
+    netd, probd, _, _ = product_setup("swap12", torch.float32)
+    with torch.no_grad():
+        sh = nb.ocflow_sums(x, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"])
+        Jh, ch = nb.OCflow(x, net, prob, [0.0, 1.0], 10, "rk4", meta["alph"], noMean=True)
+        sd = nb.ocflow_sums(x.cuda(), netd, probd, [0.0, 1.0], 10, "rk4", meta["alph"])
+        Jd, cd = nb.OCflow(x.cuda(), netd, probd, [0.0, 1.0], 10, "rk4", meta["alph"], noMean=True)
+    assert not sh.is_cuda and float(sh[7]) == 1000
+    assert torch.allclose(sh, sd.cpu(), rtol=1e-12, atol=1e-9)
+    assert torch.equal(Jh, Jd.cpu()) and all(torch.equal(a, b.cpu()) for a, b in zip(ch, cd))
+
+
 def test_config5_random_init_swarm50_shape_fp64(nb):
     """BASELINE.json configs[4]: random-init swarm50-shape Phi, full validation loss, nt = 50, fp64."""
     z = np.load(GOLDEN + "/config5.npz")
