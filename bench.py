@@ -47,8 +47,8 @@ WORKLOADS = {
 # figure is 4 d bytes per sample (the initial state is read once; mean mode writes nothing per sample); the excess is
 # register-spill / scratch-state write-back, negligible against the kernel's duration (compute-bound).
 DRAM_BYTES_PER_SAMPLE = {
-    ("swap12", "tensor"): (25.346304e6 + 18.176e6) / 262144,
-    ("singlequad", "tensor"): (12.79488e6 + 1.28e6) / 262144,
+    ("swap12", "tensor"): (25.347328e6 + 15.872e6) / 262144,
+    ("singlequad", "tensor"): (12.783872e6 + 1.024e6) / 262144,
     ("swap12", "tile"): (12.819456e6 + 256.0e6) / 131072,
     ("swarm50", "tile"): (14.542336e6 + 1.271296e6) / 16384,
 }
