@@ -134,6 +134,39 @@ def test_intermediates_across_many_tiles(nb, name, monkeypatch):
     assert torch.allclose(zf[:, d + 1, -1:], cn[2], rtol=1e-6, atol=1e-6)      # accumulated HJt
 
 
+@pytest.mark.parametrize("name,n,nt", [("softcorridor", 4096, 50), ("swap2", 4096, 50), ("swap12", 4096, 50),
+                                       ("singlequad", 4096, 50), ("swarm50", 512, 80)])
+def test_parity_gate_4096_samples(nb, name, n, nt, monkeypatch):
+    """SURVEY.md 8(d) parity gate at its stated size: 4 096 samples per problem from the benchmark distribution (512 for
+    swarm50), the documented nt, the kernel the library picks by itself (tensor cores where they apply): per-step state
+    <= 1e-5 relative against the fp32 oracle and against the fp64 oracle, mean cost terms <= 1e-4 relative (fp64 oracle)."""
+    from oracle import ocflow_oracle as orc
+    from helpers import oracle_setup, mean_vec
+    monkeypatch.delenv("NOC_FORCE_PATH", raising=False)
+    net, prob, xinit, meta = product_setup(name, torch.float32)
+    P32, D32, _, _ = oracle_setup(name, torch.float32)
+    P64, D64, _, _ = oracle_setup(name, torch.float64)
+    d = xinit.shape[1]
+    g = torch.Generator().manual_seed(1234)
+    if name == "singlequad":
+        x = torch.zeros(n, d)
+        x[:, :3] = -1.5 + meta["var0"] * torch.randn(n, 3, generator=g)
+    else:
+        x = xinit.cpu() + meta["var0"] * torch.randn(n, d, generator=g)
+    torch.set_num_threads(os.cpu_count() or 1)
+    with torch.no_grad():
+        zg, _ = nb.OCflow(x.cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        mg = mean_vec(nb.OCflow(x.cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"]))
+        z32, _ = orc.ocflow(x, P32, D32, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        z64, _ = orc.ocflow(x.double(), P64, D64, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        m64 = mean_vec(orc.ocflow(x.double(), P64, D64, [0.0, 1.0], nt, "rk4", meta["alph"]))
+    zg = zg.cpu().numpy()
+    e32, e64, ref = rel_state_err(zg, z32.numpy(), d), rel_state_err(zg, z64.numpy(), d), rel_state_err(z32.numpy(), z64.numpy(), d)
+    assert e32 <= 1e-5, "%s: state vs fp32 oracle %.2e" % (name, e32)
+    assert e64 <= max(1e-5, 2 * ref), "%s: state vs fp64 oracle %.2e (fp32 oracle itself: %.2e)" % (name, e64, ref)
+    check_costs(mg, m64, 1e-4, 2e-4, name + " mean costs vs fp64 oracle, %d samples" % n)
+
+
 def test_benchmark_scale_properties(nb, monkeypatch):
     """Size-independent properties at benchmark-like batch sizes (the oracle cannot run there): permutation invariance of
     the means, additivity of the cost sums over row shards, determinism, and mean == mean of noMean."""
