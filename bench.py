@@ -54,11 +54,13 @@ DRAM_BYTES_PER_SAMPLE = {
 }
 
 
-def tensor_flops_per_sample_step(d, m):
+def tensor_flops_per_sample_step(d, m, quadcopter):
     """bf16 tensor-core flops the tcgen05 kernel EXECUTES per sample-step (noc_tc_rollout.cuh): 4 evaluations x 6 split
-    products x 2 flops x the padded GEMM volumes  KS*mp + 2*mp*mp + mp*KS + KS*KS."""
+    products x 2 flops x the padded GEMM volumes  KS*mp + 2*mp*mp + mp*KS + KS*KS  (KS = d+2 rounded up to 16; the width is
+    padded to the epilogue chunk x threads per sample of the shape: 64 for the quadcopter shape, 16 otherwise)."""
     ks = -(-(d + 2) // 16) * 16
-    mp = -(-m // (64 if d == 12 else 16)) * (64 if d == 12 else 16)
+    pad = 64 if quadcopter else 16
+    mp = -(-m // pad) * pad
     return 4 * 6 * 2 * (ks * mp + 2 * mp * mp + mp * ks + ks * ks)
 
 
@@ -79,7 +81,7 @@ def roofline(workload, W, d, meta, n, nt, fl, step_s, fma_peak, path):
         tpeak = float(peaks.get("bf16_tflops_sustained", 0) or 0) or 2250.0
         src = ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks.get("bf16_tflops_sustained")
                else "B200_PROFILING.md fallback: nominal dense bf16 2250 TFLOP/s")
-        ach = n * nt * tensor_flops_per_sample_step(d, meta["m"]) / step_s / 1e12
+        ach = n * nt * tensor_flops_per_sample_step(d, meta["m"], meta.get("data") == "singlequad") / step_s / 1e12
         return {"bound": "tensor", "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak, "traffic": traffic,
                 "traffic_note": note, "peak_source": src, "kernel": "rollout_tc_kernel (tcgen05, 3-way bf16 split: 6 MMAs per fp32 product)",
                 "algorithmic_fp32_tflops": alg, "fp32_fma_peak_tflops": fma_peak, "algorithmic_over_fma_peak": alg / fma_peak}
