@@ -102,7 +102,9 @@ int noc_stage_times(double t0, double t1, int32_t nt, double* table);
 /*
  * noc_ocflow — replaces OCflow(x, Phi, prob, tspan, nt, stepper, alph, intermediates, noMean), src/OCflow.py:7-95,
  * i.e. stepRK4/stepRK1 (:143-184), ocOdefun (:104-140), Phi.getGrad / Phi.forward (Phi.py:91-138) and
- * prob.calcLHQW / calcGradpH / calcCtrls, as ONE persistent kernel launch (+ a 1-block finishing reduction).
+ * prob.calcLHQW / calcGradpH / calcCtrls, as ONE persistent kernel launch (+ a 1-block finishing reduction in mean mode, a
+ * weight-packing kernel for the FMA kernels, a layout transpose of the trajectories for the tensor-core kernel's
+ * intermediates mode).
  *
  *   x            dev [n, d]
  *   stage_times  HOST [nt * 5] from noc_stage_times(), or NULL to have it computed from (t0, t1, nt)
