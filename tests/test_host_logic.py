@@ -123,3 +123,20 @@ def test_dropin_hook_rebinds_reference_module():
             "from src.Phi import Phi; from src.initProb import initProb; print('hooked')")
     out = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, cwd="/tmp")
     assert out.returncode == 0 and "hooked" in out.stdout, out.stderr
+
+
+def test_bench_flop_accounting():
+    """bench.py's roofline numerators: SURVEY.md 8(d)'s algorithmic flops per sample-step, and the bf16 flops the tensor-core
+    kernel executes (6 split products over the padded GEMM volumes)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    b = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(b)
+    want = {"softcorridor": (4, 32, 19144), "swap2": (4, 16, 5576), "swap12": (24, 32, 33184), "singlequad": (12, 128, 290120),
+            "swarm50": (150, 512, 5455456)}
+    for name, (d, m, f) in want.items():
+        assert b.flops_per_sample_step(d, m, 2, min(10, d + 1)) == f, name
+    assert b.tensor_flops_per_sample_step(24, 32, False) == 4 * 6 * 2 * (32 * 32 + 2 * 32 * 32 + 32 * 32 + 32 * 32)
+    assert b.tensor_flops_per_sample_step(12, 128, True) == 4 * 6 * 2 * (16 * 128 + 2 * 128 * 128 + 128 * 16 + 16 * 16)
+    assert b.tensor_flops_per_sample_step(4, 16, False) == 4 * 6 * 2 * (16 * 16 * 5)
+    assert b.tensor_flops_per_sample_step(12, 100, True) == b.tensor_flops_per_sample_step(12, 128, True)     # width padded to 64s
