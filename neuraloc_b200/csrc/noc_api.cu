@@ -17,6 +17,7 @@
 
 #include "noc_launch.cuh"
 #include "noc_tc_rollout.cuh"
+#include "noc_ts_rollout.cuh"
 
 namespace noc {
 
@@ -514,6 +515,38 @@ static int tc_launch(int, int, int, double, const PhiRaw<double>&, const ProbPac
     return fail(NOC_ERR_UNSUPPORTED, "the tensor-core path is fp32 only");
 }
 
+// ---- streamed tensor-core path (noc_ts_rollout.cuh): fp32, nTh = 2, the 50-agent swarm with 128 < m <= 512
+int launch_ts_swarm50(const TsArgs&, const PhiRaw<float>&, int, int, int, cudaStream_t, double*);
+static bool ts_shape_ok(const noc_phi_t* ph, const noc_prob_t* pb) {
+    return ph->nTh == 2 && pb->kind == NOC_PROB_SWARMTRAJ && pb->agentDim == 3 && pb->nAgents == 50 && ph->d == 150 && ph->m > 128 &&
+           ph->m <= 512 && ts_smem_bytes_50() <= (size_t)g_smem_optin && g_cc_major == 10;
+}
+static int ts_launch(int m, int r, double h, const PhiRaw<float>& raw, const ProbPack& pr, const float* x, long long n, int d,
+                     const double* host_times, int nt, int stepper, int mode, const double* alph, double t_end, double* sums, float* a,
+                     float* b, float* c, int lim, cudaStream_t st) {
+    TsArgs A;
+    memset(&A, 0, sizeof A);
+    A.m = m; A.h = (float)h;
+    A.b1 = raw.b[1]; A.w = raw.w; A.c_w = raw.c_w; A.c_b = raw.c_b;
+    A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.mode = mode;
+    A.alph0 = (float)alph[0]; A.alph3 = (float)alph[3]; A.alph4 = (float)alph[4]; A.alph5 = (float)alph[5];
+    A.out_a = a; A.out_b = b; A.out_c = c;
+    std::vector<TcEval> ev;
+    tc_build_evals(host_times, nt, stepper, mode == NOC_MODE_INTERMEDIATES, t_end, ev);
+    TcEval* dev = nullptr;
+    NOC_CUDA(cudaMallocAsync((void**)&dev, sizeof(TcEval) * ev.size(), st));
+    NOC_CUDA(cudaMemcpyAsync(dev, ev.data(), sizeof(TcEval) * ev.size(), cudaMemcpyHostToDevice, st));
+    A.evals = dev; A.nevals = (int)ev.size();
+    int rc = launch_ts_swarm50(A, raw, d + 1, r, lim, st, sums);
+    cudaError_t e = cudaFreeAsync(dev, st);
+    if (rc == NOC_OK && e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+static int ts_launch(int, int, double, const PhiRaw<double>&, const ProbPack&, const double*, long long, int, const double*, int, int,
+                     int, const double*, double, double*, double*, double*, double*, int, cudaStream_t) {
+    return fail(NOC_ERR_UNSUPPORTED, "the tensor-core path is fp32 only");
+}
+
 template <typename real>
 static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x, int64_t n, const double* stage_times,
                        double t0, double t1, int nt, int stepper, const double* alph, int mode, void* out_costs,
@@ -557,11 +590,21 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
         if (fp && (!strcmp(fp, "tile") || !strcmp(fp, "vec"))) use_tc = false;
         if (use_tc) use_vec = false;
     }
-    g_last_path = use_tc ? NOC_PATH_TENSOR : (use_vec ? NOC_PATH_SAMPLE : NOC_PATH_TILE);
+    // streamed tensor-core kernel for the wide swarm network (same switches)
+    bool use_ts = false;
+    if (!use_tc && std::is_same<real, float>::value && ts_shape_ok(ph, pb)) {
+        const char* tc = getenv("NOC_TC");
+        const char* fp = getenv("NOC_FORCE_PATH");
+        use_ts = !use_vec && !(tc && !strcmp(tc, "0"));
+        if (fp && !strcmp(fp, "tc")) use_ts = true;
+        if (fp && (!strcmp(fp, "tile") || !strcmp(fp, "vec"))) use_ts = false;
+        if (use_ts) use_vec = false;
+    }
+    g_last_path = (use_tc || use_ts) ? NOC_PATH_TENSOR : (use_vec ? NOC_PATH_SAMPLE : NOC_PATH_TILE);
 
     int cfg_id = -1;
     size_t smem = 0;
-    if (!use_vec && !use_tc) {
+    if (!use_vec && !use_tc && !use_ts) {
         rc = choose<real>(A, dtype, pb->kind, pb->nAgents, cfg_id, smem);
         if (rc) return rc;
     }
@@ -578,7 +621,10 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     A.t_end = (real)t1;
     A.out_a = (mode == NOC_MODE_NOMEAN) ? (real*)out_costs : nullptr;
     A.out_b = (real*)zFull; A.out_c = (real*)ctrlFull;
-    if (use_tc)
+    if (use_ts)
+        rc = ts_launch(ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, ph->d, tab.data(), nt, stepper, mode, alph, t1,
+                       (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
+    else if (use_tc)
         rc = tc_launch(tc_shape, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, tab.data(), nt, stepper, mode, alph, t1,
                        (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
     else if (use_vec)

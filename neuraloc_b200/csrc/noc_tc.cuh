@@ -1,11 +1,12 @@
 // noc_tc.cuh — thin inline-PTX wrappers over the Blackwell tensor-core path (tcgen05 / TMEM) used by the probe
-// (noc_tc_probe.cu) and the tensor-core rollout kernel (noc_tc_quad.cu).  Descriptor encodings follow
+// (noc_tc_probe.cu) and the tensor-core rollout kernels (noc_tc_rollout.cuh, noc_ts_rollout.cuh).  Descriptor encodings follow
 // cute/arch/mma_sm100_desc.hpp (SmemDescriptor, InstrDescriptor); canonical no-swizzle layouts follow the comments of
 // cute/atom/mma_traits_sm100.hpp (make_umma_desc):  K-major ((8,n),2):((1,SBO),LBO),  MN-major ((1,n),(8,k)):((X,SBO),(1,LBO))
 // in 16-byte units.  Both were validated on a B200 against torch matmul (tests/test_gpu_tc_probe.py).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
+#include <cstdio>
 
 namespace noc {
 
@@ -136,5 +137,94 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy shared-memory writes (operands written by threads) -> visible to the async proxy (tensor core reads)
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair (cta_group::2) primitives used by the streamed swarm kernel (noc_ts_rollout.cuh).  Two CTAs of a cluster
+// issue ONE MMA of M = 128 (64 rows from each CTA) or M = 256; B's N rows are split between the two CTAs' shared
+// memories; each CTA's TMEM holds its own rows of D (M = 128: lanes 0-63 hold columns [0, N/2), lanes 64-127 hold
+// [N/2, N) -- the "2x2" atom of cute/atom/mma_traits_sm100.hpp: tmem_frg_2sm).  Barrier protocol after
+// cutlass/pipeline/sm100_pipeline.hpp and cutlass/arch/barrier.h (umma_arrive_multicast_2x1SM, umma_arrive_2x1SM_sm0).
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() { unsigned r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_id_x() { unsigned r; asm volatile("mov.u32 %0, %%clusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ unsigned cluster_count_x() { unsigned r; asm volatile("mov.u32 %0, %%nclusterid.x;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// shared::cluster address of `saddr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ unsigned mapa_shared(unsigned saddr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {        // release at cluster scope (data for the peer's consumer)
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
+}
+// Bounded wait: a protocol bug must not hang the GPU (a hung box is a lost lease) -- after ~4 s of spinning the kernel
+// reports which barrier it was waiting on and traps.  The clock is read once per 64 failed polls.
+static __device__ __noinline__ void mbar_timeout(unsigned mbar, int parity, int tag) {
+    printf("[noc] mbarrier wait timed out: block %d thread %d tag %d addr %u parity %d\n", (int)blockIdx.x, (int)threadIdx.x, tag, mbar, parity);
+    __trap();
+}
+__device__ __forceinline__ void mbar_wait_cluster(unsigned mbar, int parity, int tag) {   // acquire at cluster scope
+    unsigned done = 0;
+    long long t0 = 0;
+    for (unsigned it = 0; ; ++it) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+                     : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
+        if (done) break;
+        if ((it & 63) == 63) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 8000000000ll) mbar_timeout(mbar, parity, tag);
+        }
+    }
+}
+// kind::f16 instruction descriptor, fp16 x fp16 -> f32, both operands K-major
+__device__ __forceinline__ unsigned umma_idesc_f16(int M, int N) {
+    return (1u << 4) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+__device__ __forceinline__ void umma2_f16(unsigned d_tmem, unsigned long long a_desc, unsigned long long b_desc, unsigned idesc, int accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
+                 :: "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// completion of all MMAs issued so far by this thread -> one arrival on the barrier at the same offset in every CTA of `mask`
+__device__ __forceinline__ void umma2_commit_mc(unsigned mbar, unsigned short mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" :: "r"(mbar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(unsigned smem_dst, int ncols) {       // the same warp index in both CTAs of the pair
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_dst), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(unsigned taddr, int ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+// TMA: 2-D tiled load into THIS CTA's shared memory, completion bytes reported to the barrier at `mbar_cluster_addr`
+// (the pair leader's "full" barrier).  cute/arch/copy_sm100_tma.hpp: SM100_TMA_2SM_LOAD_2D.
+__device__ __forceinline__ void tma2_load_2d(unsigned dst_smem, const void* tmap, unsigned mbar_cluster_addr, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(dst_smem), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
+    asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, unsigned (&r)[8]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
+}
+// fp32 pair -> packed fp16x2 "hi" and the packed fp16x2 residual "lo": v = hi + lo to ~2^-23 |v| (fp16 has 11 significant
+// bits; the residual of a round-to-nearest fp16 is exactly representable in fp32 and again rounded to 11 bits)
+__device__ __forceinline__ void split2_f16(float a, float b, unsigned& hi, unsigned& lo) {
+    unsigned h;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));          // low half = a, high half = b
+    float ha, hb;
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n" : "=f"(ha), "=f"(hb) : "r"(h));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+    hi = h;
+}
 
 }  // namespace noc
