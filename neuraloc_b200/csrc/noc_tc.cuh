@@ -158,8 +158,12 @@ __device__ __forceinline__ unsigned mapa_shared(unsigned saddr, unsigned rank) {
     return r;
 }
 __device__ __forceinline__ void fence_mbar_init_cluster() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {        // release at cluster scope (data for the peer's consumer)
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+// Arrival on a barrier of another CTA of the cluster (cutlass/arch/barrier.h: ClusterBarrier::arrive(cta_id)).  Default
+// semantics (release, CTA scope): everything handed over through these barriers is read by the tensor core / TMA (async proxy,
+// after fence.proxy.async), never by another CTA's generic loads, so no cluster-scope fence -- which would cost a MEMBAR + ERRBAR
+// per arrival and an L1 invalidation (CCTL.IVALL) per wait: 32 % of all stall samples in the first profile of the swarm kernel.
+__device__ __forceinline__ void mbar_arrive_cluster(unsigned cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned mbar, unsigned bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(mbar), "r"(bytes) : "memory");
@@ -170,11 +174,11 @@ static __device__ __noinline__ void mbar_timeout(unsigned mbar, int parity, int 
     printf("[noc] mbarrier wait timed out: block %d thread %d tag %d addr %u parity %d\n", (int)blockIdx.x, (int)threadIdx.x, tag, mbar, parity);
     __trap();
 }
-__device__ __forceinline__ void mbar_wait_cluster(unsigned mbar, int parity, int tag) {   // acquire at cluster scope
+__device__ __forceinline__ void mbar_wait_cluster(unsigned mbar, int parity, int tag) {
     unsigned done = 0;
     long long t0 = 0;
     for (unsigned it = 0; ; ++it) {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(done) : "r"(mbar), "r"(parity) : "memory");
         if (done) break;
         if ((it & 63) == 63) {

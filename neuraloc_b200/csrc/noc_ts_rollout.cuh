@@ -61,7 +61,7 @@ struct TsShape {
     static constexpr int oB1 = oRED + (6 * 4 + 1) * 64 * 4;
     static constexpr int oWV = oB1 + MP * 4;
     static constexpr int oSRED = oWV + MP * 4;                  // [2][8] per-warp cost sums
-    static constexpr int oBAR = oSRED + 64;
+    static constexpr int oBAR = oSRED + 128;
     static constexpr int SMEM = oBAR + 32 * 8;
     // per-CTA global scratch (floats): tanh(o) [MP][64], u0 at the terminal evaluation [MP][64], z0 [d][64], RK accumulator [d][64]
     static constexpr int SCR = 2 * MP * 64 + 2 * d * 64;
@@ -240,7 +240,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
     float* sgt = sred + 6 * 4 * 64;
     float* sb1 = reinterpret_cast<float*>(smem + SH::oB1);
     float* swv = reinterpret_cast<float*>(smem + SH::oWV);
-    float* scost = reinterpret_cast<float*>(smem + SH::oSRED);
+    double* scost = reinterpret_cast<double*>(smem + SH::oSRED);
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + SH::oBAR);
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + TS_NBAR);
     const unsigned bar0 = smem_u32(bars);
@@ -286,7 +286,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
             const unsigned idN = umma_idesc_f16(128, 256), idG = umma_idesc_f16(128, KS);
             const unsigned long long dX0 = umma_desc(smem_u32(sX), 128, 2048), dS = umma_desc(smem_u32(sS), 128, SH::SBO_S);
             constexpr unsigned qX = 16384 >> 4, qS = SH::PLANE_S >> 4, slabq = 32768 >> 4;
-            unsigned wcnt = 0, xcnt[2] = {0, 0}, scnt = 0;
+            unsigned wcnt = 0, xcnt0 = 0, xcnt1 = 0, scnt = 0;
             auto wait_w = [&]() -> unsigned {
                 const unsigned slot = wcnt & 3, par = (wcnt >> 2) & 1;
                 mbar_wait_cluster(bar(TS_WFULL + slot), par, 200 + slot);
@@ -294,7 +294,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 tc_fence_after();
                 return slot;
             };
-            auto wait_x = [&](int b) { mbar_wait_cluster(bar(TS_XFULL + b), xcnt[b] & 1, 210 + b); ++xcnt[b]; tc_fence_after(); };
+            auto wait_x = [&](int b) {
+                unsigned& c = b ? xcnt1 : xcnt0;
+                mbar_wait_cluster(bar(TS_XFULL + b), c & 1, 210 + b);
+                ++c;
+                tc_fence_after();
+            };
             for (int tile = cl; tile < A.ntiles; tile += ncl)
                 for (int it = 0; it < A.nevals; ++it) {
                     const bool term = (it == A.nevals - 1);
@@ -384,7 +389,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
         const bool hasQ = (pr.obstacle != 0) && (pr.alph_Q > 0.0), hasW = (pr.alph_W != 0.0), posQ = (pr.alph_Q > 0.0);
         const float f_alphQ = float(pr.alph_Q), f_alphW = float(pr.alph_W), f_cut = float(pr.cutW), f_c2 = float(2 * pr.r * pr.r);
         const float hnet = A.h;
-        unsigned xcnt[2] = {0, 0}, acnt = 0;
+        unsigned xcnt0 = 0, xcnt1 = 0, acnt = 0;
         double csum[7] = {0, 0, 0, 0, 0, 0, 0};
         long long cnt = 0;
         const int ntp1 = A.nt + 1;
@@ -405,7 +410,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(xfull_leader + 8 * b);
         };
-        auto wait_slab_free = [&](int b) { mbar_wait_cluster(bar(TS_XEMPTY + b), (xcnt[b] & 1) ^ 1, 300 + b); ++xcnt[b]; };
+        auto wait_slab_free = [&](int b) {
+            unsigned& c = b ? xcnt1 : xcnt0;
+            mbar_wait_cluster(bar(TS_XEMPTY + b), (c & 1) ^ 1, 300 + b);
+            ++c;
+        };
         auto wait_acc = [&](int g) { mbar_wait_cluster(bar(TS_ACC + g), acnt & 1, 310 + g); tc_fence_after(); };
         // my CPT/8 chunks of the stage-input operand S = [x, t, 1, 0..] from the fp32 x in shared memory
         auto put_S = [&](float tnext) {
@@ -442,7 +451,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
             const float4* etab = reinterpret_cast<const float4*>(A.evals);
             float zq0[4] = {0.f, 0.f, 0.f, 0.f}, zqa[4] = {0.f, 0.f, 0.f, 0.f};   // [L, HJt, Q, W] integrals (gq == 3 thread)
             // ---- tile start: x -> z0 scratch, fp32 stage input, S operand of the first evaluation
-#pragma unroll 8
+#pragma unroll
             for (int i = 0; i < CPT; ++i) {
                 const int c = cbase + i;
                 if (c < d) {
@@ -580,7 +589,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     if (gq == 3) sgt[s] = g[d - ((KS / 2) + CPT)];         // Phi_t = component d of grad Phi
                     if (INTER && kind == 1) {                              // controls at the new state, OLD time (quirk 3)
                         if (valid) {
-#pragma unroll 8
+#pragma unroll
                             for (int i = 0; i < CPT; ++i) {
                                 const int c = cbase + i;
                                 if (c < d) {
@@ -595,7 +604,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         }
                     } else {
                         // RK combination of my state components (OCflow.py:143-184); dx = -grad_p H = -p (SwarmTraj.py:68-69)
-#pragma unroll 8
+#pragma unroll
                         for (int i = 0; i < CPT; ++i) {
                             const int c = cbase + i;
                             if (c < d) {
@@ -649,7 +658,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 }
                 const float* xt = static_cast<const float*>(pr.xtarget);
                 float cG = 0.f, hjg = 0.f, quad = 0.f, lin = 0.f;
-#pragma unroll 8
+#pragma unroll
                 for (int i = 0; i < CPT; ++i) {
                     const int c = cbase + i;
                     if (c < D) {
@@ -678,7 +687,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     if (A.mode == NOC_MODE_MEAN) {
 #pragma unroll
                         for (int q7 = 0; q7 < 7; ++q7) {
-                            float vsum = valid ? cost[q7] : 0.f;
+                            double vsum = valid ? (double)cost[q7] : 0.0;      // double: the sums must not depend on the tiling
 #pragma unroll
                             for (int off = 16; off > 0; off >>= 1) vsum += __shfl_xor_sync(0xffffffffu, vsum, off);
                             if (lane == 0) scost[(qd & 1) * 8 + q7] = vsum;
@@ -692,7 +701,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 }
                 ts_bar_epi();
                 if (A.mode == NOC_MODE_MEAN && warp == 6 && lane == 0) {
-                    for (int q7 = 0; q7 < 7; ++q7) csum[q7] += (double)scost[q7] + (double)scost[8 + q7];
+                    for (int q7 = 0; q7 < 7; ++q7) csum[q7] += scost[q7] + scost[8 + q7];
                     cnt += nvalid;
                 }
             }
