@@ -23,7 +23,8 @@
 // product is three MMAs (hi*hi, hi*lo, lo*hi; the dropped lo*lo term is O(2^-24)) into one fp32 TMEM accumulator.
 //
 // Warp roles (320 threads): warps 0-7 epilogue / per-sample work (4 threads per sample: TMEM lane half x column half),
-// warp 8 TMA producer (both CTAs), warp 9 MMA issuer (leader CTA only; allocates TMEM in both).
+// warp 8 TMA producer (both CTAs), warp 9 MMA issuer (leader CTA only; allocates TMEM in both).  (10 warps leave 168 registers
+// per thread; handing the two service warps' registers to the epilogue warps with setmaxnreg made ptxas spill MORE.)
 #pragma once
 #include <cuda.h>
 
@@ -61,7 +62,7 @@ struct TsShape {
     static constexpr int oB1 = oRED + (6 * 4 + 1) * 64 * 4;
     static constexpr int oWV = oB1 + MP * 4;
     static constexpr int oSRED = oWV + MP * 4;                  // [2][8] per-warp cost sums
-    static constexpr int oBAR = oSRED + 128;
+    static constexpr int oBAR = oSRED + 192;                    // + [8] running sums of this CTA
     static constexpr int SMEM = oBAR + 32 * 8;
     // per-CTA global scratch (floats): tanh(o) [MP][64], u0 at the terminal evaluation [MP][64], z0 [d][64], RK accumulator [d][64]
     static constexpr int SCR = 2 * MP * 64 + 2 * d * 64;
@@ -83,6 +84,7 @@ struct TsArgs {
     float *out_a, *out_b, *out_c;
     float* scratch;
     int ntiles;                              // tiles of 128 samples, one per CTA pair per round
+    long long* trace;                        // NOC_TS_TRACE: [4 roles][256][2] (tag, clock) of block 0 during evaluation 5, or NULL
 };
 
 // hidden unit of k-index kk (0..127) of activation slab ji (0..3): the order in which the epilogue threads produce units
@@ -222,6 +224,84 @@ __device__ __forceinline__ float ts_unbias(float v, float kq) {
 __device__ __forceinline__ float ts_unbias(float v, float) { return v; }
 #endif
 
+// Interaction cost of one sample (SwarmTraj.py:147-162): this thread owns the agent rows i = part, part + 4, ... and pairs
+// each with every j > i.  The rows are processed in blocks of up to four (i0, i0 + 4, i0 + 8, i0 + 12) so that one load of
+// agent j serves four pairs -- eight warps walking 1225 pairs per sample with three shared-memory loads per pair were bound
+// by the shared-memory pipe (which the tensor core reads its operands through as well).  Per block only the minimum squared
+// distance is tracked, branch-free; a block with a pair inside the slightly widened cut-off (rare, and the same blocks in every
+// lane: the samples of a tile are perturbations of one formation) is redone exactly -- sqrt, cut-off, exp, the "== 1" rule --
+// row by row in the reference's (i, j) order.  ts_pairs() runs the blocks whose first row lies in [ib, ie).
+__device__ __forceinline__ float ts_pair_block(const float* xs, int A, int i0, int nr, float cut, float c2, float guard, float w) {
+    float xi[4][3];
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const int i = (r < nr) ? i0 + 4 * r : i0;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) xi[r][c] = xs[(3 * i + c) * 64];
+    }
+    const int ilast = i0 + 4 * (nr - 1);
+    float dmin = guard;
+    int j = i0 + 1;
+    for (; j <= ilast && j < A; ++j) {                      // j between the rows of the block: row r pairs with j only if j > i_r
+        const float xj0 = xs[(3 * j) * 64], xj1 = xs[(3 * j + 1) * 64], xj2 = xs[(3 * j + 2) * 64];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float d0 = xi[r][0] - xj0, d1 = xi[r][1] - xj1, d2c = xi[r][2] - xj2;
+            const float d2 = fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f)));
+            if (r < nr && j > i0 + 4 * r) dmin = fminf(dmin, d2);
+        }
+    }
+    for (; j + 2 <= A; j += 2) {                           // j beyond the last row: every row of the block pairs with it
+        float xj[2][3];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) xj[u][c] = xs[(3 * (j + u) + c) * 64];
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const float d0 = xi[r][0] - xj[u][0], d1 = xi[r][1] - xj[u][1], d2c = xi[r][2] - xj[u][2];
+                dmin = fminf(dmin, fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));      // rows r >= nr repeat row 0: harmless
+            }
+    }
+    for (; j < A; ++j) {
+        const float xj0 = xs[(3 * j) * 64], xj1 = xs[(3 * j + 1) * 64], xj2 = xs[(3 * j + 2) * 64];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const float d0 = xi[r][0] - xj0, d1 = xi[r][1] - xj1, d2c = xi[r][2] - xj2;
+            dmin = fminf(dmin, fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));
+        }
+    }
+    if (dmin < guard) {
+        for (int r = 0; r < nr; ++r) {
+            const int i = i0 + 4 * r;
+            const float a0 = xs[(3 * i) * 64], a1 = xs[(3 * i + 1) * 64], a2 = xs[(3 * i + 2) * 64];
+            for (int jj = i + 1; jj < A; ++jj) {
+                const float d0 = a0 - xs[(3 * jj) * 64], d1 = a1 - xs[(3 * jj + 1) * 64], d2c = a2 - xs[(3 * jj + 2) * 64];
+                const float d2 = fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f)));
+                if (d2 < guard) {
+                    const float dd = sqrtf(d2);
+                    if (dd < cut) {
+                        const float e = r_exp(-(dd * dd) / c2);
+                        if (e != 1.f) w += e;           // pairs whose Gaussian rounds to 1 are dropped (mask2)
+                    }
+                }
+            }
+        }
+    }
+    return w;
+}
+__device__ __forceinline__ float ts_pairs(const float* xs, int A, int part, int ib, int ie, float cut, float c2, float w) {
+    const float guard = cut * cut * 1.0001f;
+    for (int i0 = ib + part; i0 < ie && i0 < A - 1; i0 += 16) {
+        int nr = (A - 1 - i0 + 3) / 4;                      // rows i0, i0 + 4, ... below A - 1
+        nr = nr > 4 ? 4 : nr;
+        w = ts_pair_block(xs, A, i0, nr, cut, c2, guard, w);
+    }
+    return w;
+}
+
 __device__ __forceinline__ void ts_bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 template <class SH, bool INTER>
@@ -245,6 +325,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
     unsigned* tmem_slot = reinterpret_cast<unsigned*>(bars + TS_NBAR);
     const unsigned bar0 = smem_u32(bars);
     auto bar = [&](int i) { return bar0 + 8u * (unsigned)i; };
+    // development aid: time stamps of one evaluation of block 0 (role 0/1: epilogue warps 0 / 7, 2: MMA issuer, 3: TMA producer)
+    // (compiled in with -DNOC_TS_TRACE_BUILD and switched on with NOC_TS_TRACE=1)
+    int trole = -1, tidx = 0;
+    bool ton = false;
+#ifdef NOC_TS_TRACE_BUILD
+    if (A.trace && blockIdx.x == 0 && lane == 0) trole = (warp == 0) ? 0 : (warp == 7 ? 1 : (warp == 9 ? 2 : (warp == 8 ? 3 : -1)));
+    auto TR = [&](int tag) {
+        if (ton && tidx < 256) { A.trace[(trole * 256 + tidx) * 2] = tag; A.trace[(trole * 256 + tidx) * 2 + 1] = clock64(); ++tidx; }
+    };
+#else
+    auto TR = [&](int) {};
+    (void)trole; (void)tidx; (void)ton;
+#endif
 
     if (tid == 0) {
         for (int i = 0; i < 4; ++i) { mbar_init(bar(TS_WFULL + i), 1); mbar_init(bar(TS_WEMPTY + i), 1); }
@@ -273,7 +366,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 for (int it = 0; it < A.nevals; ++it)
                     for (int st = 0; st < SH::NSTAGE; ++st, ++cnt) {
                         const unsigned slot = cnt & 3, par = (cnt >> 2) & 1;
+                        ton = (trole == 3 && tile == cl && it == 5);
                         mbar_wait_cluster(bar(TS_WEMPTY + slot), par ^ 1, 100 + slot);
+                        if ((st & 7) == 0) TR(st);
                         if (rank == 0) mbar_arrive_expect_tx(bar(TS_WFULL + slot), 2 * SH::STAGE_BYTES);
                         tma2_load_2d(smem_u32(sW + slot * SH::STAGE_BYTES), &tmapW, wfull_leader + 8 * slot, 0,
                                      (int)((rank * SH::NSTAGE + st) * 128));
@@ -303,9 +398,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
             for (int tile = cl; tile < A.ntiles; tile += ncl)
                 for (int it = 0; it < A.nevals; ++it) {
                     const bool term = (it == A.nevals - 1);
+                    ton = (trole == 2 && tile == cl && it == 5);
+                    TR(0);
                     // ---- GEMM-1: O = S . K0b'  -> R0, committed per instruction half
                     mbar_wait_cluster(bar(TS_SFULL), scnt & 1, 220); ++scnt;
                     tc_fence_after();
+                    TR(1);
                     for (int nh = 0; nh < 2; ++nh) {
                         for (int sp = 0; sp < KS / 32; ++sp) {
                             const unsigned slot = wait_w();
@@ -320,13 +418,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         }
                         if (elect_one_sync()) umma2_commit_mc(bar(TS_ACC + nh), 3);
                         __syncwarp();
+                        TR(10 + nh);
                     }
                     // ---- GEMM-2: A1 = U0 . K1' -> R1;  GEMM-3: Z1 = Y . K1 -> R0   (activation slabs as they are produced)
                     for (int gm = 0; gm < 2; ++gm) {
                         const unsigned Rd = gm == 0 ? R1 : R0;
                         for (int ji = 0; ji < 4; ++ji) {
                             const int b = ji & 1;
+                            TR(100 * (gm + 1) + 10 * ji);
                             wait_x(b);
+                            TR(100 * (gm + 1) + 10 * ji + 1);
                             for (int ks = 0; ks < 8; ++ks) {
                                 const unsigned slot = wait_w();
                                 if (elect_one_sync()) {
@@ -343,6 +444,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         }
                         if (elect_one_sync()) umma2_commit_mc(bar(TS_ACC + 2 + gm), 3);
                         __syncwarp();
+                        TR(100 * (gm + 1) + 50);
                     }
                     // ---- GEMM-4: G = V . K0 + S . [A'A | c_w]' -> R1 (terminal evaluation: the S part apart, at R1 + 128)
                     for (int s4 = 0; s4 < SH::NS4; ++s4) {
@@ -350,7 +452,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         for (int t = 0; t < 3; ++t) {
                             const int g = 3 * s4 + t;
                             if (g >= SH::NK4) break;
-                            if (g < 32 && (g & 7) == 0) wait_x((g >> 3) & 1);
+                            if (g < 32 && (g & 7) == 0) { TR(300 + g); wait_x((g >> 3) & 1); TR(301 + g); }
                             if (elect_one_sync()) {
                                 const unsigned long long dB = umma_desc(smem_u32(sW + slot * SH::STAGE_BYTES + t * 2 * SH::G4_PLANE), 128, 256);
                                 if (g < 32) {
@@ -368,9 +470,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     }
                     if (elect_one_sync()) umma2_commit_mc(bar(TS_ACC + 4), 3);
                     __syncwarp();
+                    TR(350);
                 }
         }
-    } else {
+    } else if (warp_u < 8) {
         // ================= epilogue / per-sample warps =================
         const int qd = warp & 3, wh = warp >> 2;
         const int s = 32 * (qd & 1) + lane, q = qd >> 1, gq = 2 * wh + q;
@@ -390,8 +493,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
         const float f_alphQ = float(pr.alph_Q), f_alphW = float(pr.alph_W), f_cut = float(pr.cutW), f_c2 = float(2 * pr.r * pr.r);
         const float hnet = A.h;
         unsigned xcnt0 = 0, xcnt1 = 0, acnt = 0;
-        double csum[7] = {0, 0, 0, 0, 0, 0, 0};
-        long long cnt = 0;
+        double* csum = scost + 16;                              // [7] cost sums + sample count of this CTA (thread warp 6, lane 0)
+        if (warp == 6 && lane < 8) csum[lane] = 0.0;
         const int ntp1 = A.nt + 1;
 
         // write 32 values (units ubase + 32 ji + [0,32)) as one thread's part of activation slab `b`, then hand the slab over
@@ -476,21 +579,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 const float tcur = ef.x, wgt = ef.y, cnext = ef.z, hstep = ef.w;
                 const int k = ei.x, kind = ei.y, first = ei.z, last = ei.w;
                 const bool term = (kind == 2);
-                // ---- problem terms that need only x (SwarmTraj.py:90-164), while GEMM-1 runs
+                ton = (trole >= 0 && trole < 2 && tile == cl && it == 5);
+                TR(0);
+                // ---- problem terms that need only x (SwarmTraj.py:90-164): computed in three pieces in the gaps where these
+                //      warps would wait for the tensor core (after each of the epilogues 1-3 the last two slabs are still in flight)
                 float qpart = 0.f, wpart = 0.f;
-                if (!term) {
-                    if (hasQ)
-                        for (int a = gq; a < SH::NA; a += 4)
-                            qpart += terrain_agent<float>(pr, sxs[(3 * a) * 64 + s], sxs[(3 * a + 1) * 64 + s], sxs[(3 * a + 2) * 64 + s]);
-                    if (hasW) wpart = interaction_pairs<3, 64, float>(sxs + s, SH::NA, gq, 4, f_cut, f_c2);
-                }
                 // ---- epilogue 1: u0 = act(o) -> slabs, tanh(o) -> scratch
+                TR(1);
                 wait_acc(wh);
+                TR(2);
 #pragma unroll 1
                 for (int ji = 0; ji < 4; ++ji) {
                     float v[32], tt[32];
                     tmem_ld32(R0 + lane_bits + colH + 32 * ji, v);
+                    TR(100 + 10 * ji);
                     wait_slab_free(ji & 1);
+                    TR(101 + 10 * ji);
 #pragma unroll
                     for (int i = 0; i < 32; ++i) act_tanh(ts_unbias(v[i], kq1) * is1, v[i], tt[i]);
                     const int g4 = ((ubase + 32 * ji) >> 2) * 64 + s;
@@ -504,12 +608,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 }
                 // ---- epilogue 2: y = tanh(a1 + b1) * w -> slabs   (terminal: also w . (u0 + h act(a1 + b1)), Phi.py:50,96)
                 float phiN = 0.f;
+                if (!term) {
+                    if (hasQ)
+                        for (int a = gq; a < SH::NA; a += 4)
+                            qpart += terrain_agent<float>(pr, sxs[(3 * a) * 64 + s], sxs[(3 * a + 1) * 64 + s], sxs[(3 * a + 2) * 64 + s]);
+                    if (hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 0, 16, f_cut, f_c2, wpart);
+                }
+                TR(150);
                 wait_acc(2);
+                TR(151);
 #pragma unroll 1
                 for (int ji = 0; ji < 4; ++ji) {
                     float v[32];
                     tmem_ld32(R1 + lane_bits + colH + 32 * ji, v);
+                    TR(200 + 10 * ji);
                     wait_slab_free(ji & 1);
+                    TR(201 + 10 * ji);
                     const int u0i = ubase + 32 * ji;
                     if (term) {
                         const int g4 = (u0i >> 2) * 64 + s;
@@ -539,7 +653,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     put_slab(ji & 1, v);
                 }
                 // ---- epilogue 3: v = tanh(o) * (w + h z1) -> slabs
+                if (!term && hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 16, 32, f_cut, f_c2, wpart);
+                TR(250);
                 wait_acc(3);
+                TR(251);
                 const float hs = hnet * is2;
 #pragma unroll 1
                 for (int ji = 0; ji < 4; ++ji) {
@@ -549,7 +666,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
 #pragma unroll
                     for (int i = 0; i < 8; ++i) t4[i] = __ldcg(t0s + g4 + 64 * i);
                     tmem_ld32(R0 + lane_bits + colH + 32 * ji, v);
+                    TR(300 + 10 * ji);
                     wait_slab_free(ji & 1);
+                    TR(301 + 10 * ji);
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const float4 w4 = *reinterpret_cast<const float4*>(swv + u0i + 4 * i);
@@ -561,7 +680,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     put_slab(ji & 1, v);
                 }
                 // ---- epilogue 4: grad Phi -> costs, RK update, next stage input
+                float z0v[CPT];                                      // step-start state of my components: loads in flight during the
+#pragma unroll                                                       // last piece of the pair loop
+                for (int i = 0; i < CPT; ++i) {
+                    const int c = cbase + i;
+                    z0v[i] = (c < d && !term) ? __ldcg(z0s + c * 64 + s) : 0.f;
+                }
+                if (!term && hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 32, SH::NA, f_cut, f_c2, wpart);
+                TR(350);
                 wait_acc(4);
+                TR(351);
                 ++acnt;
                 float g[CPT];
                 {
@@ -593,7 +721,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                             for (int i = 0; i < CPT; ++i) {
                                 const int c = cbase + i;
                                 if (c < d) {
-                                    A.out_b[(gs * NZ + c) * ntp1 + k + 1] = __ldcg(z0s + c * 64 + s);
+                                    A.out_b[(gs * NZ + c) * ntp1 + k + 1] = z0v[i];
                                     A.out_c[(gs * d + c) * ntp1 + k + 1] = -g[i];
                                 }
                             }
@@ -603,23 +731,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                             }
                         }
                     } else {
-                        // RK combination of my state components (OCflow.py:143-184); dx = -grad_p H = -p (SwarmTraj.py:68-69)
+                        // RK combination of my state components (OCflow.py:143-184); dx = -grad_p H = -p (SwarmTraj.py:68-69).
+                        // The RK accumulator comes from the scratch in two batches of CPT / 2 loads (register budget).
 #pragma unroll
-                        for (int i = 0; i < CPT; ++i) {
-                            const int c = cbase + i;
-                            if (c < d) {
-                                const float kk = hstep * (-g[i]);
-                                const float z0v = __ldcg(z0s + c * 64 + s);
-                                const float zav = (first ? z0v : __ldcg(zas + c * 64 + s)) + wgt * kk;
-                                float xn;
-                                if (!last) { __stcg(zas + c * 64 + s, zav); xn = z0v + cnext * kk; }
-                                else { __stcg(z0s + c * 64 + s, zav); xn = zav; }
-                                sxs[c * 64 + s] = xn;
+                        for (int hb = 0; hb < 2; ++hb) {
+                            float zav[CPT / 2];
+#pragma unroll
+                            for (int i = 0; i < CPT / 2; ++i) {
+                                const int c = cbase + hb * (CPT / 2) + i;
+                                zav[i] = (c < d && !first) ? __ldcg(zas + c * 64 + s) : 0.f;
+                            }
+#pragma unroll
+                            for (int i = 0; i < CPT / 2; ++i) {
+                                const int ii = hb * (CPT / 2) + i, c = cbase + ii;
+                                if (c < d) {
+                                    const float kk = hstep * (-g[ii]);
+                                    const float za1 = (first ? z0v[ii] : zav[i]) + wgt * kk;
+                                    float xn;
+                                    if (!last) { __stcg(zas + c * 64 + s, za1); xn = z0v[ii] + cnext * kk; }
+                                    else { __stcg(z0s + c * 64 + s, za1); xn = za1; }
+                                    sxs[c * 64 + s] = xn;
+                                }
                             }
                         }
                     }
+                    TR(400);
                     put_S(__ldg(etab + 2 * (it + 1)).x);
+                    TR(401);
                     ts_bar_epi();
+                    TR(402);
                     if (gq == 3 && !(INTER && kind == 1)) {                // L, H, the four cost rates (SwarmTraj.py:71-87, OCflow.py:130-138)
                         float pps = 0.f, qs = 0.f, ws = 0.f;
 #pragma unroll
@@ -637,6 +777,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         }
                     }
                     arrive_S();
+                    TR(403);
                     continue;
                 }
                 // ---- terminal block (OCflow.py:58-90): x(T) in shared memory, g = grad Phi(x(T), T)
@@ -702,13 +843,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 ts_bar_epi();
                 if (A.mode == NOC_MODE_MEAN && warp == 6 && lane == 0) {
                     for (int q7 = 0; q7 < 7; ++q7) csum[q7] += scost[q7] + scost[8 + q7];
-                    cnt += nvalid;
+                    csum[7] += (double)nvalid;
                 }
             }
         }
         if (A.mode == NOC_MODE_MEAN && A.partials && warp == 6 && lane == 0) {
-            for (int q7 = 0; q7 < 7; ++q7) A.partials[blockIdx.x * 8 + q7] = csum[q7];
-            A.partials[blockIdx.x * 8 + 7] = (double)cnt;
+            for (int q7 = 0; q7 < 8; ++q7) A.partials[blockIdx.x * 8 + q7] = csum[q7];
         }
     }
     tc_fence_before();
@@ -798,9 +938,28 @@ int launch_ts(TsArgs A, const PhiRaw<float>& raw, int D, int r, int smem_limit, 
     if (getenv("NOC_DEBUG"))
         fprintf(stderr, "[noc] ts rollout: smem=%zu grid=%d (clusters of 2) tiles=%d stages/eval=%d evals=%d\n", smem, grid, A.ntiles,
                 SH::NSTAGE, A.nevals);
+    long long* trace = nullptr;
+    if (getenv("NOC_TS_TRACE")) {
+        NOC_CUDA(cudaMalloc((void**)&trace, sizeof(long long) * 4 * 256 * 2));
+        NOC_CUDA(cudaMemset(trace, 0, sizeof(long long) * 4 * 256 * 2));
+        A.trace = trace;
+    }
     kern<<<grid, SH::NT, smem, st>>>(A, tmap);
     count_launch();
     NOC_CUDA(cudaGetLastError());
+    if (trace) {
+        std::vector<long long> h(4 * 256 * 2);
+        NOC_CUDA(cudaStreamSynchronize(st));
+        NOC_CUDA(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
+        long long t0 = 0;
+        for (int r = 0; r < 4; ++r) for (int i = 0; i < 256; ++i) { long long c = h[(r * 256 + i) * 2 + 1]; if (c && (!t0 || c < t0)) t0 = c; }
+        for (int r = 0; r < 4; ++r) {
+            fprintf(stderr, "[noc trace] role %d:", r);
+            for (int i = 0; i < 256 && h[(r * 256 + i) * 2 + 1]; ++i) fprintf(stderr, " %lld@%lld", h[(r * 256 + i) * 2], h[(r * 256 + i) * 2 + 1] - t0);
+            fprintf(stderr, "\n");
+        }
+        cudaFree(trace);
+    }
     if (partials) {
         int frc = launch_finish(partials, grid, out_sums, st);
         if (frc) return frc;
