@@ -531,6 +531,14 @@ static int ts_launch(int m, int r, double h, const PhiRaw<float>& raw, const Pro
     A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.mode = mode;
     A.alph0 = (float)alph[0]; A.alph3 = (float)alph[3]; A.alph4 = (float)alph[4]; A.alph5 = (float)alph[5];
     A.out_a = a; A.out_b = b; A.out_c = c;
+    A.f_alphQ = (float)pr.alph_Q; A.f_alphW = (float)pr.alph_W; A.f_cut = (float)pr.cutW; A.f_c2 = (float)(2 * pr.r * pr.r);
+    A.hasQ = (pr.obstacle != 0) && (pr.alph_Q > 0.0); A.hasW = (pr.alph_W != 0.0); A.posQ = (pr.alph_Q > 0.0);
+    A.obstacle = pr.obstacle; A.training = pr.training;
+    {
+        const double r = pr.r;                     // SwarmTraj.py:101-119: the boxes inflated by r (train mode)
+        const double t[10] = {2.0 + r, -2.0 - r, 0.5 + r, -0.5 - r, 7.0 + r, 4.0 + r, 2.0 - r, 1.0 + r, -1.0 - r, 4.0 + r};
+        for (int i = 0; i < 10; ++i) A.thr[i] = (float)t[i];
+    }
     std::vector<TcEval> ev;
     tc_build_evals(host_times, nt, stepper, mode == NOC_MODE_INTERMEDIATES, t_end, ev);
     TcEval* dev = nullptr;

@@ -28,6 +28,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <type_traits>
+
 #include "noc_launch.cuh"
 #include "noc_tc.cuh"
 #include "noc_tc_rollout.cuh"
@@ -84,7 +86,10 @@ struct TsArgs {
     float *out_a, *out_b, *out_c;
     float* scratch;
     int ntiles;                              // tiles of 128 samples, one per CTA pair per round
-    long long* trace;                        // NOC_TS_TRACE: [4 roles][256][2] (tag, clock) of block 0 during evaluation 5, or NULL
+    // problem constants rounded to fp32 on the host (a double compare / convert in the loop costs ~50x an fp32 instruction here)
+    float f_alphQ, f_alphW, f_cut, f_c2, thr[10];
+    int hasQ, hasW, posQ, obstacle, training;
+    long long* trace;                        // NOC_TS_TRACE: [20 roles][256][2] (tag, clock) of blocks 0-1 during evaluation 5, or NULL
 };
 
 // hidden unit of k-index kk (0..127) of activation slab ji (0..3): the order in which the epilogue threads produce units
@@ -240,7 +245,7 @@ __device__ __forceinline__ float ts_pair_block(const float* xs, int A, int i0, i
         for (int c = 0; c < 3; ++c) xi[r][c] = xs[(3 * i + c) * 64];
     }
     const int ilast = i0 + 4 * (nr - 1);
-    float dmin = guard;
+    float dm[4] = {guard, guard, guard, guard};            // one running minimum per row: four short dependency chains
     int j = i0 + 1;
     for (; j <= ilast && j < A; ++j) {                      // j between the rows of the block: row r pairs with j only if j > i_r
         const float xj0 = xs[(3 * j) * 64], xj1 = xs[(3 * j + 1) * 64], xj2 = xs[(3 * j + 2) * 64];
@@ -248,21 +253,22 @@ __device__ __forceinline__ float ts_pair_block(const float* xs, int A, int i0, i
         for (int r = 0; r < 4; ++r) {
             const float d0 = xi[r][0] - xj0, d1 = xi[r][1] - xj1, d2c = xi[r][2] - xj2;
             const float d2 = fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f)));
-            if (r < nr && j > i0 + 4 * r) dmin = fminf(dmin, d2);
+            if (r < nr && j > i0 + 4 * r) dm[r] = fminf(dm[r], d2);
         }
     }
-    for (; j + 2 <= A; j += 2) {                           // j beyond the last row: every row of the block pairs with it
-        float xj[2][3];
+#pragma unroll 1
+    for (; j + 4 <= A; j += 4) {                           // j beyond the last row: every row of the block pairs with it
+        float xj[4][3];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int c = 0; c < 3; ++c) xj[u][c] = xs[(3 * (j + u) + c) * 64];
 #pragma unroll
-        for (int u = 0; u < 2; ++u)
+        for (int u = 0; u < 4; ++u)
 #pragma unroll
             for (int r = 0; r < 4; ++r) {
                 const float d0 = xi[r][0] - xj[u][0], d1 = xi[r][1] - xj[u][1], d2c = xi[r][2] - xj[u][2];
-                dmin = fminf(dmin, fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));      // rows r >= nr repeat row 0: harmless
+                dm[r] = fminf(dm[r], fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));   // rows r >= nr repeat row 0: harmless
             }
     }
     for (; j < A; ++j) {
@@ -270,23 +276,35 @@ __device__ __forceinline__ float ts_pair_block(const float* xs, int A, int i0, i
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
             const float d0 = xi[r][0] - xj0, d1 = xi[r][1] - xj1, d2c = xi[r][2] - xj2;
-            dmin = fminf(dmin, fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));
+            dm[r] = fminf(dm[r], fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))));
         }
     }
-    if (dmin < guard) {
-        for (int r = 0; r < nr; ++r) {
-            const int i = i0 + 4 * r;
-            const float a0 = xs[(3 * i) * 64], a1 = xs[(3 * i + 1) * 64], a2 = xs[(3 * i + 2) * 64];
-            for (int jj = i + 1; jj < A; ++jj) {
-                const float d0 = a0 - xs[(3 * jj) * 64], d1 = a1 - xs[(3 * jj + 1) * 64], d2c = a2 - xs[(3 * jj + 2) * 64];
-                const float d2 = fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f)));
-                if (d2 < guard) {
-                    const float dd = sqrtf(d2);
-                    if (dd < cut) {
-                        const float e = r_exp(-(dd * dd) / c2);
-                        if (e != 1.f) w += e;           // pairs whose Gaussian rounds to 1 are dropped (mask2)
+    // exact pass over the rows that have a pair inside the guard (four distances per branch), in (i, j) order
+#pragma unroll 1
+    for (int r = 0; r < nr; ++r) {
+        const float dmr = (r == 0) ? dm[0] : (r == 1 ? dm[1] : (r == 2 ? dm[2] : dm[3]));
+        if (!(dmr < guard)) continue;
+        const int i = i0 + 4 * r;
+        const float a0 = xs[(3 * i) * 64], a1 = xs[(3 * i + 1) * 64], a2 = xs[(3 * i + 2) * 64];
+#pragma unroll 1
+        for (int jj = i + 1; jj < A; jj += 4) {
+            float d2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int jc = (jj + u < A) ? jj + u : A - 1;
+                const float d0 = a0 - xs[(3 * jc) * 64], d1 = a1 - xs[(3 * jc + 1) * 64], d2c = a2 - xs[(3 * jc + 2) * 64];
+                d2[u] = (jj + u < A) ? fmaf(d2c, d2c, fmaf(d1, d1, fmaf(d0, d0, 0.f))) : guard;
+            }
+            if (fminf(fminf(d2[0], d2[1]), fminf(d2[2], d2[3])) < guard) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (d2[u] < guard) {
+                        const float dd = sqrtf(d2[u]);
+                        if (dd < cut) {
+                            const float e = r_exp(-(dd * dd) / c2);
+                            if (e != 1.f) w += e;       // pairs whose Gaussian rounds to 1 are dropped (mask2)
+                        }
                     }
-                }
             }
         }
     }
@@ -300,6 +318,23 @@ __device__ __forceinline__ float ts_pairs(const float* xs, int A, int part, int 
         w = ts_pair_block(xs, A, i0, nr, cut, c2, guard, w);
     }
     return w;
+}
+
+// Per-agent terrain cost of SwarmTraj ('blocks', SwarmTraj.py:90-122) with the problem constants in registers.  (The shared
+// terrain_agent() takes the problem descriptor by reference: here that put a copy of the kernel parameter in local memory and
+// every field read became an L2 round trip -- 7 000 cycles per evaluation for 13 agents in the first trace.)
+__device__ __forceinline__ float ts_terrain(int obstacle, bool training, const float (&t)[10], float x0, float x1, float x2) {
+    if (obstacle != 3) return 0.f;
+    if (!training) {                    // bitwise &, |: no short-circuit branches (ten dependent branches per agent otherwise)
+        const bool in = ((x0 < 2.0f) & (x0 > -2.0f) & (x1 < 0.5f) & (x1 > -0.5f) & (x2 < 7.0f)) |
+                        ((x0 < 4.0f) & (x0 > 2.0f) & (x1 < 1.0f) & (x1 > -1.0f) & (x2 < 4.0f));
+        return in ? 1.f : 0.f;
+    }
+    // thresholds inflated by r, rounded from double on the host: t = {2+r, -2-r, .5+r, -.5-r, 7+r, 4+r, 2-r, 1+r, -1-r, 4+r}
+    const bool in = ((x0 < t[0]) & (x0 > t[1]) & (x1 < t[2]) & (x1 > t[3]) & (x2 < t[4])) |
+                    ((x0 < t[5]) & (x0 > t[6]) & (x1 < t[7]) & (x1 > t[8]) & (x2 < t[9]));
+    if (!in) return 0.f;
+    return (gauss3<float>(x0, x1, x2, 0.f, 0.f, 2.f, 9.f, 3.f, 9.f) + gauss3<float>(x0, x1, x2, 2.5f, 0.f, 2.f, 9.f, 3.f, 3.f)) + 999.f;
 }
 
 __device__ __forceinline__ void ts_bar_epi() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
@@ -330,7 +365,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
     int trole = -1, tidx = 0;
     bool ton = false;
 #ifdef NOC_TS_TRACE_BUILD
-    if (A.trace && blockIdx.x == 0 && lane == 0) trole = (warp == 0) ? 0 : (warp == 7 ? 1 : (warp == 9 ? 2 : (warp == 8 ? 3 : -1)));
+    if (A.trace && blockIdx.x < 2 && lane == 0) trole = (int)blockIdx.x * 10 + warp;     // role = 10 * CTA + warp (8: TMA, 9: MMA)
     auto TR = [&](int tag) {
         if (ton && tidx < 256) { A.trace[(trole * 256 + tidx) * 2] = tag; A.trace[(trole * 256 + tidx) * 2 + 1] = clock64(); ++tidx; }
     };
@@ -366,7 +401,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 for (int it = 0; it < A.nevals; ++it)
                     for (int st = 0; st < SH::NSTAGE; ++st, ++cnt) {
                         const unsigned slot = cnt & 3, par = (cnt >> 2) & 1;
-                        ton = (trole == 3 && tile == cl && it == 5);
+                        ton = (trole % 10 == 8 && tile == cl && it == 5);
                         mbar_wait_cluster(bar(TS_WEMPTY + slot), par ^ 1, 100 + slot);
                         if ((st & 7) == 0) TR(st);
                         if (rank == 0) mbar_arrive_expect_tx(bar(TS_WFULL + slot), 2 * SH::STAGE_BYTES);
@@ -398,7 +433,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
             for (int tile = cl; tile < A.ntiles; tile += ncl)
                 for (int it = 0; it < A.nevals; ++it) {
                     const bool term = (it == A.nevals - 1);
-                    ton = (trole == 2 && tile == cl && it == 5);
+                    ton = (trole % 10 == 9 && tile == cl && it == 5);
                     TR(0);
                     // ---- GEMM-1: O = S . K0b'  -> R0, committed per instruction half
                     mbar_wait_cluster(bar(TS_SFULL), scnt & 1, 220); ++scnt;
@@ -489,9 +524,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
         const float is1 = A.scales[3], is2 = A.scales[4], is4 = A.scales[5];
         const float kq1 = A.scales[6], kq2 = A.scales[7], kq4 = A.scales[8];
         const unsigned xfull_leader = mapa_shared(bar(TS_XFULL), 0), sfull_leader = mapa_shared(bar(TS_SFULL), 0);
-        const bool hasQ = (pr.obstacle != 0) && (pr.alph_Q > 0.0), hasW = (pr.alph_W != 0.0), posQ = (pr.alph_Q > 0.0);
-        const float f_alphQ = float(pr.alph_Q), f_alphW = float(pr.alph_W), f_cut = float(pr.cutW), f_c2 = float(2 * pr.r * pr.r);
+        const bool hasQ = A.hasQ != 0, hasW = A.hasW != 0, posQ = A.posQ != 0;
+        const float f_alphQ = A.f_alphQ, f_alphW = A.f_alphW, f_cut = A.f_cut, f_c2 = A.f_c2;
         const float hnet = A.h;
+        const int p_obstacle = A.obstacle;
+        const bool p_training = A.training != 0;
         unsigned xcnt0 = 0, xcnt1 = 0, acnt = 0;
         double* csum = scost + 16;                              // [7] cost sums + sample count of this CTA (thread warp 6, lane 0)
         if (warp == 6 && lane < 8) csum[lane] = 0.0;
@@ -579,7 +616,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 const float tcur = ef.x, wgt = ef.y, cnext = ef.z, hstep = ef.w;
                 const int k = ei.x, kind = ei.y, first = ei.z, last = ei.w;
                 const bool term = (kind == 2);
-                ton = (trole >= 0 && trole < 2 && tile == cl && it == 5);
+                ton = (trole >= 0 && trole % 10 < 8 && tile == cl && it == 5);
                 TR(0);
                 // ---- problem terms that need only x (SwarmTraj.py:90-164): computed in three pieces in the gaps where these
                 //      warps would wait for the tensor core (after each of the epilogues 1-3 the last two slabs are still in flight)
@@ -608,10 +645,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 }
                 // ---- epilogue 2: y = tanh(a1 + b1) * w -> slabs   (terminal: also w . (u0 + h act(a1 + b1)), Phi.py:50,96)
                 float phiN = 0.f;
+                TR(140);
                 if (!term) {
                     if (hasQ)
                         for (int a = gq; a < SH::NA; a += 4)
-                            qpart += terrain_agent<float>(pr, sxs[(3 * a) * 64 + s], sxs[(3 * a + 1) * 64 + s], sxs[(3 * a + 2) * 64 + s]);
+                            qpart += ts_terrain(p_obstacle, p_training, A.thr, sxs[(3 * a) * 64 + s], sxs[(3 * a + 1) * 64 + s], sxs[(3 * a + 2) * 64 + s]);
+                    TR(141);
                     if (hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 0, 16, f_cut, f_c2, wpart);
                 }
                 TR(150);
@@ -680,12 +719,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     put_slab(ji & 1, v);
                 }
                 // ---- epilogue 4: grad Phi -> costs, RK update, next stage input
-                float z0v[CPT];                                      // step-start state of my components: loads in flight during the
-#pragma unroll                                                       // last piece of the pair loop
-                for (int i = 0; i < CPT; ++i) {
-                    const int c = cbase + i;
-                    z0v[i] = (c < d && !term) ? __ldcg(z0s + c * 64 + s) : 0.f;
-                }
                 if (!term && hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 32, SH::NA, f_cut, f_c2, wpart);
                 TR(350);
                 wait_acc(4);
@@ -707,6 +740,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
 #pragma unroll
                     for (int i = 0; i < 32; ++i) g[i] = ts_unbias(__uint_as_float(r32[i]), kq4) * is4;
                 }
+                TR(360);
                 if (!term) {
                     float pp = 0.f;
 #pragma unroll
@@ -715,13 +749,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     sred[(1 * 4 + gq) * 64 + s] = qpart;
                     sred[(2 * 4 + gq) * 64 + s] = wpart;
                     if (gq == 3) sgt[s] = g[d - ((KS / 2) + CPT)];         // Phi_t = component d of grad Phi
+                    TR(370);
                     if (INTER && kind == 1) {                              // controls at the new state, OLD time (quirk 3)
                         if (valid) {
 #pragma unroll
                             for (int i = 0; i < CPT; ++i) {
                                 const int c = cbase + i;
                                 if (c < d) {
-                                    A.out_b[(gs * NZ + c) * ntp1 + k + 1] = z0v[i];
+                                    A.out_b[(gs * NZ + c) * ntp1 + k + 1] = __ldcg(z0s + c * 64 + s);
                                     A.out_c[(gs * d + c) * ntp1 + k + 1] = -g[i];
                                 }
                             }
@@ -732,28 +767,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                         }
                     } else {
                         // RK combination of my state components (OCflow.py:143-184); dx = -grad_p H = -p (SwarmTraj.py:68-69).
-                        // The RK accumulator comes from the scratch in two batches of CPT / 2 loads (register budget).
+                        // z0 / the RK accumulator come from the L2 scratch in four batches, the next batch's loads in flight while
+                        // this one is combined (no long-lived register arrays: they spilled, and a spill is an L2 round trip here).
+                        constexpr int NB = (CPT == 40) ? 5 : 4, BQ = CPT / NB;
+                        auto rk = [&](auto FIRST, auto LAST) {
+                            constexpr bool F = decltype(FIRST)::value, L = decltype(LAST)::value;
+                            float zb[2][BQ], za2[2][BQ];
+                            auto fetch = [&](int b, float (&a0)[BQ], float (&a1)[BQ]) {
 #pragma unroll
-                        for (int hb = 0; hb < 2; ++hb) {
-                            float zav[CPT / 2];
+                                for (int i = 0; i < BQ; ++i) {
+                                    const int c = cbase + b * BQ + i;
+                                    a0[i] = (c < d && (F || !L)) ? __ldcg(z0s + c * 64 + s) : 0.f;
+                                    a1[i] = (c < d && !F) ? __ldcg(zas + c * 64 + s) : 0.f;
+                                }
+                            };
+                            fetch(0, zb[0], za2[0]);
 #pragma unroll
-                            for (int i = 0; i < CPT / 2; ++i) {
-                                const int c = cbase + hb * (CPT / 2) + i;
-                                zav[i] = (c < d && !first) ? __ldcg(zas + c * 64 + s) : 0.f;
-                            }
+                            for (int b = 0; b < NB; ++b) {
+                                if (b + 1 < NB) fetch(b + 1, zb[(b + 1) & 1], za2[(b + 1) & 1]);
 #pragma unroll
-                            for (int i = 0; i < CPT / 2; ++i) {
-                                const int ii = hb * (CPT / 2) + i, c = cbase + ii;
-                                if (c < d) {
-                                    const float kk = hstep * (-g[ii]);
-                                    const float za1 = (first ? z0v[ii] : zav[i]) + wgt * kk;
-                                    float xn;
-                                    if (!last) { __stcg(zas + c * 64 + s, za1); xn = z0v[ii] + cnext * kk; }
-                                    else { __stcg(z0s + c * 64 + s, za1); xn = za1; }
-                                    sxs[c * 64 + s] = xn;
+                                for (int i = 0; i < BQ; ++i) {
+                                    const int ii = b * BQ + i, c = cbase + ii;
+                                    if (c < d) {
+                                        const float kk = hstep * (-g[ii]);
+                                        const float za1 = (F ? zb[b & 1][i] : za2[b & 1][i]) + wgt * kk;
+                                        float xn;
+                                        if (!L) { __stcg(zas + c * 64 + s, za1); xn = zb[b & 1][i] + cnext * kk; }
+                                        else { __stcg(z0s + c * 64 + s, za1); xn = za1; }
+                                        sxs[c * 64 + s] = xn;
+                                    }
                                 }
                             }
-                        }
+                        };
+                        if (first) { if (last) rk(std::true_type{}, std::true_type{}); else rk(std::true_type{}, std::false_type{}); }
+                        else { if (last) rk(std::false_type{}, std::true_type{}); else rk(std::false_type{}, std::false_type{}); }
                     }
                     TR(400);
                     put_S(__ldg(etab + 2 * (it + 1)).x);
@@ -940,20 +987,20 @@ int launch_ts(TsArgs A, const PhiRaw<float>& raw, int D, int r, int smem_limit, 
                 SH::NSTAGE, A.nevals);
     long long* trace = nullptr;
     if (getenv("NOC_TS_TRACE")) {
-        NOC_CUDA(cudaMalloc((void**)&trace, sizeof(long long) * 4 * 256 * 2));
-        NOC_CUDA(cudaMemset(trace, 0, sizeof(long long) * 4 * 256 * 2));
+        NOC_CUDA(cudaMalloc((void**)&trace, sizeof(long long) * 20 * 256 * 2));
+        NOC_CUDA(cudaMemset(trace, 0, sizeof(long long) * 20 * 256 * 2));
         A.trace = trace;
     }
     kern<<<grid, SH::NT, smem, st>>>(A, tmap);
     count_launch();
     NOC_CUDA(cudaGetLastError());
     if (trace) {
-        std::vector<long long> h(4 * 256 * 2);
+        std::vector<long long> h(20 * 256 * 2);
         NOC_CUDA(cudaStreamSynchronize(st));
         NOC_CUDA(cudaMemcpy(h.data(), trace, sizeof(long long) * h.size(), cudaMemcpyDeviceToHost));
         long long t0 = 0;
-        for (int r = 0; r < 4; ++r) for (int i = 0; i < 256; ++i) { long long c = h[(r * 256 + i) * 2 + 1]; if (c && (!t0 || c < t0)) t0 = c; }
-        for (int r = 0; r < 4; ++r) {
+        for (int r = 0; r < 20; ++r) for (int i = 0; i < 256; ++i) { long long c = h[(r * 256 + i) * 2 + 1]; if (c && (!t0 || c < t0)) t0 = c; }
+        for (int r = 0; r < 20; ++r) {
             fprintf(stderr, "[noc trace] role %d:", r);
             for (int i = 0; i < 256 && h[(r * 256 + i) * 2 + 1]; ++i) fprintf(stderr, " %lld@%lld", h[(r * 256 + i) * 2], h[(r * 256 + i) * 2 + 1] - t0);
             fprintf(stderr, "\n");
