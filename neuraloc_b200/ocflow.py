@@ -22,7 +22,6 @@ import torch
 from . import _cabi
 
 _PACK_CACHE = weakref.WeakKeyDictionary()     # Phi module -> {(device, dtype): (signature, tensors, PhiT, keepalive)}
-_XT_CACHE = {}
 
 
 def _require_cuda():
@@ -38,8 +37,19 @@ def _dtype_code(dt):
     raise ValueError("OCflow supports float32 and float64 tensors (--prec single|double), got %s" % dt)
 
 
+def invalidate_cache(Phi=None):
+    """Drop the cached device copies of a module's weights (all modules if None).  The cache key is (data_ptr, _version, dtype,
+    device) of every parameter: load_state_dict, optimizers and in-place ops on the parameters are seen; in-place edits made
+    through `p.data` are NOT (Tensor.data has its own version counter) — call this after such edits."""
+    if Phi is None:
+        _PACK_CACHE.clear()
+    else:
+        _PACK_CACHE.pop(Phi, None)
+
+
 def _phi_struct(Phi, device, dtype):
-    """Flatten the live module into noc_phi_t (device copies in `dtype`; cached until a parameter changes)."""
+    """Flatten the live module into noc_phi_t (device copies in `dtype`; cached until a parameter changes, see
+    invalidate_cache)."""
     layers = list(Phi.N.layers)
     tensors = [Phi.A, Phi.c.weight, Phi.c.bias, Phi.w.weight] + [l.weight for l in layers] + [l.bias for l in layers]
     sig = tuple((t.data_ptr(), t._version, t.dtype, str(t.device)) for t in tensors)
@@ -71,14 +81,9 @@ def _prob_struct(prob, device, dtype):
             obstacle = None        # Quadcopter.calcObstacle ignores unknown obstacles (Quadcopter.py:115-122)
         else:
             raise ValueError("unsupported obstacle %r" % (obstacle,))
-    xt = prob.xtarget.detach().reshape(-1)
-    key = (xt.data_ptr(), xt._version, str(device), dtype, xt.numel())
-    xdev = _XT_CACHE.get(key)
-    if xdev is None:
-        if len(_XT_CACHE) > 64:
-            _XT_CACHE.clear()
-        xdev = xt.to(device=device, dtype=dtype).contiguous()
-        _XT_CACHE[key] = xdev
+    # xtarget is d numbers: upload it on every call when it is not already a device tensor of the rollout dtype (a cache keyed
+    # on the source's address could hand back another problem's target after the allocator reuses the address)
+    xdev = prob.xtarget.detach().reshape(-1).to(device=device, dtype=dtype).contiguous()
     st = _cabi.ProbT(kind=_cabi.PROB_KINDS[name], obstacle=_cabi.OBSTACLES[obstacle], training=int(bool(prob.training)),
                      nAgents=int(prob.nAgents), agentDim=int(prob.agentDim), alph_Q=float(prob.alph_Q),
                      alph_W=float(prob.alph_W), r=float(prob.r), mass=float(getattr(prob, "mass", 1.0)),

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import (DT, GOLDEN, PROBLEMS, check_costs, load_cases, load_ckpt, mean_vec, oracle_setup, product_setup,
+from helpers import (DT, GOLDEN, PROBLEMS, QW, check_costs, load_cases, load_ckpt, mean_vec, oracle_setup, product_setup,
                      rel_err, rel_state_err)
 
 pytestmark = pytest.mark.gpu
@@ -41,7 +41,10 @@ def _three_modes(nb, x, net, prob, tspan, nt, stepper, alph):
     return mean, nomean, zf.cpu().numpy(), cf.cpu().numpy()
 
 
-def _compare(tag, d, got, ref, what, state_tol=None):
+def _compare(tag, d, got, ref, what, state_tol=None, truth=None):
+    """`ref` = the reference's outputs in the run's own precision (mean, noMean, zFull, ctrlFull); `truth` = the same from the
+    reference's fp64 run (fp32 runs only): the cost terms are then gated against the fp64 values at 1e-4 relative or twice the
+    reference's own fp32<->fp64 distance, whichever is larger — no absolute floor except for Q and W."""
     tol = dict(TOL[tag])
     if state_tol is not None:
         tol["state"] = state_tol
@@ -55,19 +58,27 @@ def _compare(tag, d, got, ref, what, state_tol=None):
     assert not cf[:, :, 0].any()
     cerr = np.abs(cf - rc).max() / max(np.abs(rc).max(), 1.0)
     assert cerr <= tol["ctrl"], "%s: controls rel err %.3e" % (what, cerr)
+    tmean, tnomean = (truth[0], truth[1]) if truth is not None else (None, None)
     if rmean is not None:
-        # a single sample's G = 0.5|x(T)-x_tgt|^2 (~1e-3) and HJgrad are pure cancellation: the reference's own fp32 and
-        # fp64 runs differ by up to 1e-3 there, so the 1e-4 gate applies to means over >= 6 samples
-        loose = (zf.shape[0] == 1)
-        idx = [0, 1, 3, 4, 6, 7] if loose else list(range(8))
-        check_costs(mean[idx], rmean[idx], tol["cost"], tol["floor"], what + " mean costs")
-        if loose:
-            check_costs(mean[[2, 5]], rmean[[2, 5]], 20 * tol["cost"], tol["floor"], what + " G / HJgrad of one sample")
+        if tmean is not None:
+            check_costs(mean, tmean, tol["cost"], tol["floor"], what + " mean costs vs the reference's fp64 run", floor_mask=QW,
+                        ref_noise=np.asarray(rmean, dtype=np.float64) - np.asarray(tmean, dtype=np.float64))
+        else:
+            check_costs(mean, rmean, tol["cost"], tol["floor"], what + " mean costs", floor_mask=QW)
     if rnomean is not None:
-        sc = np.maximum(np.abs(rnomean).max(axis=0, keepdims=True), 1.0)
-        assert (np.abs(nomean - rnomean) / sc).max() <= 30 * tol["cost"], what + " per-sample costs"
+        # per-sample costs: relative to the largest entry of the column, at 30x the mean tolerance or three times the
+        # reference's own fp32<->fp64 distance in that column (a single sample's G and HJgrad are pure cancellation, H2)
+        base = tnomean if tnomean is not None else rnomean
+        sc = np.maximum(np.abs(base).max(axis=0, keepdims=True), 1e-30)
+        lim = np.full(base.shape[1], 30 * tol["cost"])
+        if tnomean is not None:
+            lim = np.maximum(lim, 3.0 * (np.abs(np.asarray(rnomean, dtype=np.float64) - tnomean) / sc).max(axis=0))
+        perr = (np.abs(nomean - base) / sc).max(axis=0)
+        keep = np.abs(base).max(axis=0) > 0          # all-zero columns (Q, W off the obstacles): exact match required below
+        assert (perr[keep] <= lim[keep]).all(), "%s per-sample costs: %s (limits %s)" % (what, perr, lim)
+        assert (np.abs(nomean[:, ~keep]) <= tol["floor"]).all(), what + " per-sample Q / W where the reference has none"
         # noMean table is consistent with the means
-        check_costs(nomean.mean(axis=0), mean, 10 * tol["cost"], tol["floor"], what + " noMean vs mean")
+        check_costs(nomean.mean(axis=0), mean, 10 * tol["cost"], tol["floor"], what + " noMean vs mean", floor_mask=QW)
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -79,10 +90,13 @@ def test_rollout_golden(nb, name, tag):
     d = xinit.shape[1]
     nt = int(c["nt"])
     got = _three_modes(nb, xinit, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"])
-    _compare(tag, d, got, (c["xinit_mean_" + tag], None, c["xinit_z_" + tag], c["xinit_ctrl_" + tag]), name + " xInit")
+    truth = (lambda pre: (c[pre + "_mean_f64"], c[pre + "_nomean_f64"] if pre + "_nomean_f64" in c.files else None)) if tag == "f32" else None
+    _compare(tag, d, got, (c["xinit_mean_" + tag], None, c["xinit_z_" + tag], c["xinit_ctrl_" + tag]), name + " xInit",
+             truth=truth("xinit") if truth else None)
     xb = torch.from_numpy(c["xb"]).to(DT[tag]).cuda()
     got = _three_modes(nb, xb, net, prob, [0.0, 1.0], int(c["nt_batch"]), "rk4", meta["alph"])
-    _compare(tag, d, got, (c["b_mean_" + tag], c["b_nomean_" + tag], c["b_z_" + tag], c["b_ctrl_" + tag]), name + " batch")
+    _compare(tag, d, got, (c["b_mean_" + tag], c["b_nomean_" + tag], c["b_z_" + tag], c["b_ctrl_" + tag]), name + " batch",
+             truth=truth("b") if truth else None)
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -194,7 +208,7 @@ def test_rollout_vs_oracle_ragged_batches(nb, name):
         print("%s n=%d: CUDA fp32 vs fp64 oracle %.2e, vs fp32 oracle %.2e" % (name, n, e64, e32))
         assert e64 <= 1e-5 and e32 <= 1e-5, (name, n, e64, e32)
         check_costs(mean[1:6], ref_nm[:n, 1:6].mean(axis=0), 1e-4, 1e-6, "%s n=%d mean costs vs fp64 oracle" % (name, n))
-        check_costs(mean[6:], ref_nm[:n, 6:].mean(axis=0), 1e-4, 2e-4, "%s n=%d Q/W" % (name, n))
+        check_costs(mean[6:], ref_nm[:n, 6:].mean(axis=0), 1e-4, 2e-4, "%s n=%d Q/W" % (name, n), floor_mask=[True, True])
 
 
 @pytest.mark.parametrize("cfg", [0, 1, 2, 3, 4, 5, 6, 7, 8])
@@ -269,7 +283,8 @@ def test_cpu_tensors_take_the_host_entry_point(nb):
         Jc, cs = nb.OCflow(xinit, net, prob, [0.0, 1.0], 50, "rk4", meta["alph"])
         zf, cf = nb.OCflow(xinit, net, prob, [0.0, 1.0], 50, "rk4", meta["alph"], intermediates=True)
     assert not Jc.is_cuda and not zf.is_cuda and Jc.dim() == 0 and Jc.dtype == torch.float32
-    check_costs(mean_vec((Jc, cs)), c["xinit_mean_f32"], 1e-4, 2e-4, "host path")
+    check_costs(mean_vec((Jc, cs)), c["xinit_mean_f64"], 1e-4, 2e-4, "host path", floor_mask=QW,
+                ref_noise=c["xinit_mean_f32"].astype(np.float64) - c["xinit_mean_f64"])
     assert rel_state_err(zf.numpy(), c["xinit_z_f32"], 4) <= 1e-5
     assert "{:e}".format(Jc) and float(cs[0].item()) > 0          # the drivers format with {:e} and .item()
 
@@ -308,7 +323,7 @@ def test_config5_random_init_swarm50_shape_fp64(nb):
     prob.eval()
     x = torch.from_numpy(z["x"]).cuda()
     mean, nomean, zf, cf = _three_modes(nb, x, net, prob, [0.0, 1.0], 50, "rk4", alph)
-    check_costs(mean, z["mean_f64"], 1e-9, 1e-9, "config 5 validation loss")
+    check_costs(mean, z["mean_f64"], 1e-9, 1e-9, "config 5 validation loss", floor_mask=QW)
     assert rel_err(zf[:, :150, -1], z["z_last_f64"][:, :150], floor=1e-3) <= 1e-10
     assert rel_err(cf[:, :, -1], z["ctrl_last_f64"], floor=1.0) <= 1e-9
     sc = np.maximum(np.abs(z["nomean_f64"]).max(axis=0, keepdims=True), 1.0)
@@ -327,7 +342,7 @@ def test_default_path_selection_by_batch_size(nb, monkeypatch):
         a = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], 20, "rk4", meta["alph"]))
         monkeypatch.setenv("NOC_VEC_MAX", "10")
         b = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], 20, "rk4", meta["alph"]))
-    check_costs(a, b, 2e-5, 1e-5, "vec vs tile path")
+    check_costs(a, b, 2e-5, 1e-5, "vec vs tile path", floor_mask=QW)
     assert not np.array_equal(a, b)          # different kernels, different summation orders
 
 

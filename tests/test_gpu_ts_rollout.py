@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import DT, check_costs, load_cases, mean_vec, oracle_setup, product_setup, rel_state_err
+from helpers import DT, QW, check_costs, load_cases, mean_vec, oracle_setup, product_setup, rel_state_err
 from test_gpu_parity import _compare, _three_modes
 
 pytestmark = pytest.mark.gpu
@@ -32,7 +32,8 @@ def test_ts_rollout_golden(nb):
     d = xinit.shape[1]
     got = _three_modes(nb, xinit, net, prob, [0.0, 1.0], int(c["nt"]), "rk4", meta["alph"])
     assert nb._cabi.last_path() == "tensor"
-    _compare("f32", d, got, (c["xinit_mean_f32"], None, c["xinit_z_f32"], c["xinit_ctrl_f32"]), "ts swarm50 xInit")
+    _compare("f32", d, got, (c["xinit_mean_f32"], None, c["xinit_z_f32"], c["xinit_ctrl_f32"]), "ts swarm50 xInit",
+             truth=(c["xinit_mean_f64"], None))
     xb = torch.from_numpy(c["xb"]).float().cuda()
     got = _three_modes(nb, xb, net, prob, [0.0, 1.0], int(c["nt_batch"]), "rk4", meta["alph"])
     # nt = 20 on the adversarial rows is ill-conditioned in fp32 (the reference's own fp32 run is far from its fp64 run):
@@ -80,7 +81,7 @@ def test_ts_vs_oracle_ragged(nb, n, nt, tspan):
     assert not cf[:, :, 0].any()
     assert np.abs(cf - c64.numpy()).max() <= 2e-4 * max(1.0, float(c64.abs().max()))
     check_costs(mean[:6], m64[:6], 1e-4, 0.0, "ts mean costs (Jc, L, G, HJt, HJfin, HJgrad) vs fp64 oracle, n=%d" % n)
-    check_costs(mean[6:], m64[6:], 1e-4, 2e-4, "ts mean Q, W")
+    check_costs(mean[6:], m64[6:], 1e-4, 2e-4, "ts mean Q, W", floor_mask=[True, True])
     n64 = torch.cat([J64] + list(cs64), 1).numpy()
     sc = np.maximum(np.abs(n64).max(axis=0, keepdims=True), 1e-30)
     perr = (np.abs(nomean - n64) / sc).max(axis=0)
@@ -110,7 +111,7 @@ def test_ts_many_tiles_subsampled_oracle(nb):
     tab = torch.cat([J] + list(cs), 1).double().cpu().numpy()
     assert float(s_all[7]) == n
     assert torch.allclose(s_all, lo + hi, rtol=1e-9, atol=1e-6)
-    check_costs((s_all[:7] / n).cpu().numpy(), tab[:, 1:].mean(axis=0), 1e-6, 1e-7, "mean mode vs mean of noMean")
+    check_costs((s_all[:7] / n).cpu().numpy(), tab[:, 1:].mean(axis=0), 1e-6, 1e-7, "mean mode vs mean of noMean", floor_mask=QW[1:])
     idx = torch.linspace(0, n - 1, 256).long()
     xs = x[idx.cuda()].cpu()
     torch.set_num_threads(os.cpu_count() or 1)

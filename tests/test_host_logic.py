@@ -136,7 +136,22 @@ def test_bench_flop_accounting():
             "swarm50": (150, 512, 5455456)}
     for name, (d, m, f) in want.items():
         assert b.flops_per_sample_step(d, m, 2, min(10, d + 1)) == f, name
-    assert b.tensor_flops_per_sample_step(24, 32, False) == 4 * 6 * 2 * (32 * 32 + 2 * 32 * 32 + 32 * 32 + 32 * 32)
-    assert b.tensor_flops_per_sample_step(12, 128, True) == 4 * 6 * 2 * (16 * 128 + 2 * 128 * 128 + 128 * 16 + 16 * 16)
-    assert b.tensor_flops_per_sample_step(4, 16, False) == 4 * 6 * 2 * (16 * 16 * 5)
-    assert b.tensor_flops_per_sample_step(12, 100, True) == b.tensor_flops_per_sample_step(12, 128, True)     # width padded to 64s
+    assert b.tensor_flops_per_sample_step("swap12", 24, 32)[0] == 4 * 6 * 2 * (32 * 32 + 2 * 32 * 32 + 32 * 32 + 32 * 32)
+    assert b.tensor_flops_per_sample_step("singlequad", 12, 128)[0] == 4 * 6 * 2 * (16 * 128 + 2 * 128 * 128 + 128 * 16 + 16 * 16)
+    assert b.tensor_flops_per_sample_step("swap2", 4, 16)[0] == 4 * 6 * 2 * (16 * 16 * 5)
+    assert b.tensor_flops_per_sample_step("singlequad", 12, 100)[0] == b.tensor_flops_per_sample_step("singlequad", 12, 128)[0]   # width padded to 64s
+    # streamed swarm kernel: 3 split products (fp16 x 2), KS = 160, m = 512
+    assert b.tensor_flops_per_sample_step("swarm50", 150, 512)[0] == 4 * 3 * 2 * (2 * 160 * 512 + 2 * 512 * 512 + 160 * 160)
+    # the default workload is the north_star target shape, strong-scaled; shards cover the batch exactly
+    assert b.DEFAULT_WORKLOAD == "swarm50" and b.WORKLOADS["swarm50"]["scaling"] == "strong"
+    for world in (1, 2, 3, 8):
+        rows = [b.shard(1000003, world, r) for r in range(world)]
+        assert rows[0][0] == 0 and rows[-1][1] == 1000003 and all(rows[i][1] == rows[i + 1][0] for i in range(world - 1))
+
+
+def test_bench_does_not_import_test_helpers_or_oracle_at_import():
+    """bench.py's GPU arm must not depend on tests/ or on the oracle (only the cpu_baseline / reference legs import oracle/)."""
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert "from helpers import" not in src and "import helpers" not in src
+    head = src.split("def cpu_rate")[0]
+    assert "oracle" not in head.replace("oracle/ocflow_oracle.py", "").replace("CPU oracle port", "").replace("the oracle", "")
