@@ -71,15 +71,15 @@ def mean_vec(out):
 QW = np.array([False] * 6 + [True, True])      # positions of Q, W in the 8-vector [Jc, L, G, HJt, HJfin, HJgrad, Q, W]
 
 
-def check_costs(got, ref, rel, abs_floor, what="", floor_mask=None, ref_noise=None):
+def check_costs(got, ref, rel, abs_floor, what="", floor_mask=None, ref_noise=None, noise_mult=2.0):
     """|got - ref| <= rel * |ref| per entry.  `abs_floor` applies ONLY to the entries selected by `floor_mask` (Q and W, which
     are 0 or tiny on most inputs: SURVEY.md H2/H3) — L, G, HJt, HJfin, HJgrad and Jc are gated relatively, G included.
-    `ref_noise` (same shape) widens an entry's tolerance to twice the reference's own fp32<->fp64 distance there."""
+    `ref_noise` (same shape) widens an entry's tolerance to `noise_mult` (2) times the reference's own fp32<->fp64 distance there."""
     got, ref = np.asarray(got, dtype=np.float64), np.asarray(ref, dtype=np.float64)
     err = np.abs(got - ref)
     tol = rel * np.abs(ref)
     if ref_noise is not None:
-        tol = np.maximum(tol, 2.0 * np.abs(np.asarray(ref_noise, dtype=np.float64)))
+        tol = np.maximum(tol, noise_mult * np.abs(np.asarray(ref_noise, dtype=np.float64)))
     ok = err <= tol
     if floor_mask is not None:
         ok = ok | (np.asarray(floor_mask, dtype=bool) & (err <= abs_floor))

@@ -61,8 +61,11 @@ def _compare(tag, d, got, ref, what, state_tol=None, truth=None):
     tmean, tnomean = (truth[0], truth[1]) if truth is not None else (None, None)
     if rmean is not None:
         if tmean is not None:
+            # one sample alone: G (~1e-4..1e-2) and HJgrad are pure cancellation and every fp32 summation order lands somewhere
+            # else inside the fp32 noise: 8x the reference's own fp32<->fp64 distance there; batches (means): 2x
             check_costs(mean, tmean, tol["cost"], tol["floor"], what + " mean costs vs the reference's fp64 run", floor_mask=QW,
-                        ref_noise=np.asarray(rmean, dtype=np.float64) - np.asarray(tmean, dtype=np.float64))
+                        ref_noise=np.asarray(rmean, dtype=np.float64) - np.asarray(tmean, dtype=np.float64),
+                        noise_mult=8.0 if zf.shape[0] == 1 else 2.0)
         else:
             check_costs(mean, rmean, tol["cost"], tol["floor"], what + " mean costs", floor_mask=QW)
     if rnomean is not None:
