@@ -178,9 +178,16 @@ def test_path_selection(nb, monkeypatch):
         monkeypatch.delenv("NOC_TC")
         nb.OCflow(x.double(), net.double(), product_setup("swap12", torch.float64)[1], [0.0, 1.0], 4, "rk4", meta["alph"])
         assert nb._cabi.last_path() == "tile"                      # fp64 has no tensor-core kernel
-        monkeypatch.setenv("NOC_FORCE_PATH", "tc")
         net5, prob5, xinit5, meta5 = product_setup("swarm50", torch.float32)
         Jc, cs = nb.OCflow(xinit5.repeat(300, 1), net5, prob5, [0.0, 1.0], 4, "rk4", meta5["alph"])
+        assert nb._cabi.last_path() == "tensor" and np.isfinite(float(Jc))      # the streamed CTA-pair kernel (m = 512)
+        monkeypatch.setenv("NOC_TC", "0")
+        nb.OCflow(xinit5.repeat(300, 1), net5, prob5, [0.0, 1.0], 4, "rk4", meta5["alph"])
+        assert nb._cabi.last_path() == "tile"
+        monkeypatch.delenv("NOC_TC")
+        monkeypatch.setenv("NOC_FORCE_PATH", "tc")
+        net6, prob6, xinit6, meta6 = product_setup("swarm50", torch.float64)     # a shape / dtype without a tensor kernel
+        Jc, cs = nb.OCflow(xinit6.repeat(300, 1), net6, prob6, [0.0, 1.0], 4, "rk4", meta6["alph"])
         assert nb._cabi.last_path() == "tile" and np.isfinite(float(Jc))
 
 
