@@ -720,6 +720,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                 }
                 // ---- epilogue 4: grad Phi -> costs, RK update, next stage input
                 if (!term && hasW) wpart = ts_pairs(sxs + s, SH::NA, gq, 32, SH::NA, f_cut, f_c2, wpart);
+                // every warp is done reading this evaluation's x (pair terms) and the previous evaluation's partial sums before
+                // any warp overwrites them below: GEMM-4's completion does not imply it (the slabs it needs were handed over
+                // before the last piece of the pair loop).  compute-sanitizer racecheck found this one.
+                ts_bar_epi();
                 TR(350);
                 wait_acc(4);
                 TR(351);
