@@ -84,6 +84,7 @@ struct TsArgs {
     float alph0, alph3, alph4, alph5;
     double* partials;
     float *out_a, *out_b, *out_c;
+    float* stage;                            // intermediates: tile-major staging [tile][step][row][128 samples] (coalesced), or NULL
     float* scratch;
     int ntiles;                              // tiles of 128 samples, one per CTA pair per round
     // problem constants rounded to fp32 on the host (a double compare / convert in the loop costs ~50x an fp32 instruction here)
@@ -533,6 +534,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
         double* csum = scost + 16;                              // [7] cost sums + sample count of this CTA (thread warp 6, lane 0)
         if (warp == 6 && lane < 8) csum[lane] = 0.0;
         const int ntp1 = A.nt + 1;
+        // intermediates: trajectory column `col` of row c of (zFull | ctrlFull).  With the staging buffer a warp writes 128
+        // contiguous bytes per (step, row) and tc_untile_kernel transposes into the reference layout [n, rows, nt+1] afterwards;
+        // without it (allocation failed) every thread writes its strided 4-byte element.
+        auto put_z = [&](int tile, long long gs, int c, int col, float v) {
+            if (A.stage) A.stage[(((size_t)tile * ntp1 + col) * (NZ + d) + c) * 128 + 64 * rank + s] = v;
+            else A.out_b[(gs * NZ + c) * ntp1 + col] = v;
+        };
+        auto put_u = [&](int tile, long long gs, int c, int col, float v) {
+            if (A.stage) A.stage[(((size_t)tile * ntp1 + col) * (NZ + d) + NZ + c) * 128 + 64 * rank + s] = v;
+            else A.out_c[(gs * d + c) * ntp1 + col] = v;
+        };
 
         // write 32 values (units ubase + 32 ji + [0,32)) as one thread's part of activation slab `b`, then hand the slab over
         auto put_slab = [&](int b, const float* v) {
@@ -598,12 +610,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                     const float xv = A.x[gs * d + c];
                     __stcg(z0s + c * 64 + s, xv);
                     sxs[c * 64 + s] = xv;
-                    if (INTER && valid) { A.out_b[(gs * NZ + c) * ntp1] = xv; A.out_c[(gs * d + c) * ntp1] = 0.f; }
+                    if (INTER && valid) { put_z(tile, gs, c, 0, xv); put_u(tile, gs, c, 0, 0.f); }
                 }
             }
             if (INTER && valid && gq == 3) {
 #pragma unroll
-                for (int c = d; c < NZ; ++c) A.out_b[(gs * NZ + c) * ntp1] = 0.f;
+                for (int c = d; c < NZ; ++c) put_z(tile, gs, c, 0, 0.f);
             }
             put_S(__ldg(etab).x);
             ts_bar_epi();
@@ -760,13 +772,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(SH::NT, 1) rollout_t
                             for (int i = 0; i < CPT; ++i) {
                                 const int c = cbase + i;
                                 if (c < d) {
-                                    A.out_b[(gs * NZ + c) * ntp1 + k + 1] = __ldcg(z0s + c * 64 + s);
-                                    A.out_c[(gs * d + c) * ntp1 + k + 1] = -g[i];
+                                    put_z(tile, gs, c, k + 1, __ldcg(z0s + c * 64 + s));
+                                    put_u(tile, gs, c, k + 1, -g[i]);
                                 }
                             }
                             if (gq == 3) {
 #pragma unroll
-                                for (int c = 0; c < 4; ++c) A.out_b[(gs * NZ + d + c) * ntp1 + k + 1] = zq0[c];
+                                for (int c = 0; c < 4; ++c) put_z(tile, gs, d + c, k + 1, zq0[c]);
                             }
                         }
                     } else {
@@ -989,6 +1001,14 @@ int launch_ts(TsArgs A, const PhiRaw<float>& raw, int D, int r, int smem_limit, 
     if (getenv("NOC_DEBUG"))
         fprintf(stderr, "[noc] ts rollout: smem=%zu grid=%d (clusters of 2) tiles=%d stages/eval=%d evals=%d\n", smem, grid, A.ntiles,
                 SH::NSTAGE, A.nevals);
+    // intermediates: stage the trajectories tile-major (coalesced) and transpose afterwards; if the staging buffer (as large as
+    // the outputs) cannot be allocated the kernel writes the reference layout directly (strided, slower, same result)
+    float* stage = nullptr;
+    if (A.mode == NOC_MODE_INTERMEDIATES && !getenv("NOC_TS_NOSTAGE")) {
+        const size_t bytes = sizeof(float) * (size_t)A.ntiles * (A.nt + 1) * (SH::NZ + SH::d) * 128;
+        if (cudaMallocAsync((void**)&stage, bytes, st) != cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
+    }
+    A.stage = stage;
     long long* trace = nullptr;
     if (getenv("NOC_TS_TRACE")) {
         NOC_CUDA(cudaMalloc((void**)&trace, sizeof(long long) * 20 * 256 * 2));
@@ -1010,6 +1030,12 @@ int launch_ts(TsArgs A, const PhiRaw<float>& raw, int D, int r, int smem_limit, 
             fprintf(stderr, "\n");
         }
         cudaFree(trace);
+    }
+    if (stage) {
+        tc_untile_kernel<<<dim3(A.ntiles, SH::NZ + SH::d), 128, 0, st>>>(stage, A.out_b, A.out_c, A.n, A.nt + 1, SH::NZ, SH::d);
+        count_launch();
+        NOC_CUDA(cudaGetLastError());
+        NOC_CUDA(cudaFreeAsync(stage, st));
     }
     if (partials) {
         int frc = launch_finish(partials, grid, out_sums, st);

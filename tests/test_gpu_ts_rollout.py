@@ -123,3 +123,20 @@ def test_ts_many_tiles_subsampled_oracle(nb):
     perr = (np.abs(got - n64) / sc).max(axis=0)
     assert (perr[[0, 1, 3, 4]] <= 1e-4).all() and perr[2] <= 3e-3 and perr[5] <= 3e-3, "per-sample costs vs fp64 oracle: %s" % perr
     check_costs(got.mean(axis=0)[:6], n64.mean(axis=0)[:6], 1e-4, 0.0, "means over the 256 sub-sampled rows vs fp64 oracle")
+
+
+def test_ts_intermediates_staged_equals_direct(nb, monkeypatch):
+    """intermediates=True: the tile-major staging buffer + transpose (coalesced) gives bit-identical zFull / ctrlFull to the
+    direct strided writes (the fallback when the staging buffer cannot be allocated); ragged batch, several tiles per CTA pair."""
+    net, prob, xinit, meta = product_setup("swarm50", torch.float32)
+    d = xinit.shape[1]
+    g = torch.Generator().manual_seed(8)
+    x = (xinit.cpu() + 0.1 * torch.randn(128 * 74 + 301, d, generator=g)).cuda()
+    with torch.no_grad():
+        za, ca = nb.OCflow(x, net, prob, [0.0, 1.0], 3, "rk4", meta["alph"], intermediates=True)
+        monkeypatch.setenv("NOC_TS_NOSTAGE", "1")
+        zb, cb = nb.OCflow(x, net, prob, [0.0, 1.0], 3, "rk4", meta["alph"], intermediates=True)
+    assert nb._cabi.last_path() == "tensor"
+    assert za.shape == (x.shape[0], d + 4, 4) and ca.shape == (x.shape[0], d, 4)
+    assert torch.equal(za, zb) and torch.equal(ca, cb)
+    assert torch.equal(za[:, :d, 0], x) and not ca[:, :, 0].any() and not za[:, d:, 0].any()
