@@ -154,6 +154,20 @@ int noc_measure_fma_peak(int32_t dtype, double* tflops);
 int noc_tc_probe(const void* A_bf16, const void* B_bf16, void* D_f32, int32_t N, int32_t K, int32_t b_mn_major,
                  int32_t roundtrip_tmem, void* stream);
 
+/* noc_sample_rho0 — replaces the host-side draw of the initial states, `xInit + cvt(var0 * torch.randn(n, d))`
+ * (src/initProb.py:27-28,107-120,196-203 and resample, :252-262; the quadcopter perturbs its first 3 columns only, :132-140):
+ *   x[i, c] = center[c] + (c < noise_cols ? var0 * N(0,1) : 0)   for the rows row0 .. row0 + n - 1 of the (virtual) full batch.
+ * Counter-based Philox4x32-10 + Box-Muller: row i, column c uses word (i d + c) % 4 of counter block (i d + c) / 4 under
+ * key = seed, so a shard (row0, n) reproduces exactly its rows of the full batch and the result does not depend on the
+ * launch geometry.  The stream differs from torch's generators: parity with the reference is distributional (tests).
+ *   center dev [d] dtype-typed; x dev [n, d]; noise_cols < 0 or > d means d. */
+int noc_sample_rho0(const void* center, int32_t d, int32_t noise_cols, double var0, uint64_t seed, int64_t row0, int64_t n,
+                    int32_t dtype, void* x, void* stream);
+
+/* The raw generator behind noc_sample_rho0 (known-answer tests): out_u32 dev [4 * ngroups] = Philox4x32-10 of the
+ * counter blocks group0 .. group0 + ngroups - 1 (counter = (lo32, hi32, 0, 0), key = (lo32(seed), hi32(seed))). */
+int noc_philox_raw(uint64_t seed, int64_t group0, int64_t ngroups, void* out_u32, void* stream);
+
 /* Which kernel family the calling thread's last noc_ocflow / noc_ocflow_host call ran (-1 before the first call):
  * the FMA sample-tile kernel, the one-CTA-per-sample small-batch kernel, or the tensor-core kernel.  The choice is made
  * from the shapes and the batch size; env NOC_TC=0 disables the tensor-core kernel, NOC_FORCE_PATH=tile|vec|tc pins one. */

@@ -20,7 +20,7 @@ MODE_MEAN, MODE_NOMEAN, MODE_INTERMEDIATES = 0, 1, 2
 # every symbol include/noc_b200.h declares (tests check the library exports exactly these)
 SYMBOLS = ["noc_version", "noc_last_error", "noc_device_info", "noc_ctrl_dim", "noc_stage_times", "noc_ocflow",
            "noc_ocflow_host", "noc_phi_eval", "noc_prob_eval", "noc_measure_fma_peak", "noc_tc_probe", "noc_launch_count",
-           "noc_last_path"]
+           "noc_last_path", "noc_sample_rho0", "noc_philox_raw"]
 
 
 class PhiT(C.Structure):
@@ -66,6 +66,8 @@ def lib():
     L.noc_prob_eval.argtypes = [C.POINTER(ProbT), vp, vp, i64, i32, i32, vp, vp, vp, vp]
     L.noc_measure_fma_peak.argtypes = [i32, C.POINTER(dbl)]
     L.noc_tc_probe.argtypes = [vp, vp, vp, i32, i32, i32, i32, vp]
+    L.noc_sample_rho0.argtypes = [vp, i32, i32, dbl, C.c_uint64, i64, i64, i32, vp, vp]
+    L.noc_philox_raw.argtypes = [C.c_uint64, i64, i64, vp, vp]
     for name in SYMBOLS:
         if name not in ("noc_last_error", "noc_launch_count"):
             getattr(L, name).restype = C.c_int

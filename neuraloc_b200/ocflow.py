@@ -230,6 +230,26 @@ def prob_eval(prob, x, p):
     return o1.to(x.device), o2.to(x.device), o3.to(x.device)
 
 
+def OCflow_shock(x, Phi, prob, nt, shockspec, stepper="rk4", alph=[1.0, 1.0, 1.0, 1.0, 1.0, 1.0]):
+    """The shock / re-planning experiment of src/plotter.py:815-823 (evalOC.py:113-120) for a whole batch, device-resident:
+    roll out to t_s = shockspec[0] with nShock = int(t_s * nt) steps, displace every state by shockspec[1] (a [1,d] row, as in
+    evalOC.py, or one row per sample [n,d]), and let the closed loop recover over [t_s, 1] with 1 + nt - nShock steps.
+
+    returns  traj1 [n,d+4,nShock+1], ctrl1, traj2 [n,d+4,nt-nShock+2], ctrl2   (the reference concatenates traj1[:, :d] and
+             traj2[:, :d] along time; the four cost integrals of each leg start at 0, as in the reference's two calls)
+    Both legs run on x's device; nothing but the two launches happens in between (no host round trip of the trajectories)."""
+    prec, shock = float(shockspec[0]), shockspec[1]
+    nt = int(nt)
+    nShock = int(prec * nt)
+    if nShock < 1 or nShock > nt:
+        raise ValueError("shock time %g leaves no step on one side of it for nt = %d" % (prec, nt))
+    d = x.shape[1]
+    traj1, ctrl1 = OCflow(x, Phi, prob, [0.0, prec], nShock, stepper, alph, intermediates=True)
+    xs = traj1[:, :d, -1] + torch.as_tensor(shock, dtype=x.dtype, device=traj1.device).reshape(-1, d)
+    traj2, ctrl2 = OCflow(xs.contiguous(), Phi, prob, [prec, 1.0], 1 + nt - nShock, stepper, alph, intermediates=True)
+    return traj1, ctrl1, traj2, ctrl2
+
+
 # ---- names other reference scripts import from src.OCflow (compareCorridor.py:18, baseline2D.py:9) ----------
 def ocG(z, xtarget):
     """G residual x - xtarget (src/OCflow.py:97-101); trivial host-side helper kept for importers."""

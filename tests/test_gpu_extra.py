@@ -282,3 +282,28 @@ def test_benchmark_scale_properties(nb, monkeypatch):
     means = (s_all[:7] / n).cpu().numpy()
     nm = torch.cat(list(cn), 1).double().mean(0).cpu().numpy()
     check_costs(means, nm, 1e-6, 1e-7, "mean mode vs mean of noMean", floor_mask=QW[1:])
+
+
+def test_batched_shock_restart(nb, monkeypatch):
+    """plotter.py:815-823 for a batch: the two legs of OCflow_shock against the oracle's two calls (fp64), with the reference's
+    minor and major softcorridor shocks (evalOC.py:115-118) applied per row."""
+    from oracle import ocflow_oracle as orc
+    from helpers import oracle_setup
+    monkeypatch.delenv("NOC_FORCE_PATH", raising=False)
+    net, prob, xinit, meta = product_setup("softcorridor", torch.float32)
+    P64, D64, _, _ = oracle_setup("softcorridor", torch.float64)
+    g = torch.Generator().manual_seed(21)
+    n, nt = 700, 50
+    x = xinit.cpu() + 0.3 * torch.randn(n, 4, generator=g)
+    shock = torch.where(torch.arange(n).view(-1, 1) % 2 == 0, torch.tensor([[-0.2, -0.7, -0.0, -0.6]]), torch.tensor([[-1.4, -1.0, -5.2, -2.8]]))
+    with torch.no_grad():
+        t1, c1, t2, c2 = nb.OCflow_shock(x.cuda(), net, prob, nt, [0.1, shock], "rk4", meta["alph"])
+        r1, _ = orc.ocflow(x.double(), P64, D64, [0.0, 0.1], 5, "rk4", meta["alph"], intermediates=True)
+        xs = r1[:, :4, -1] + shock.double()
+        r2, rc2 = orc.ocflow(xs, P64, D64, [0.1, 1.0], 46, "rk4", meta["alph"], intermediates=True)
+    assert t1.shape == (n, 8, 6) and t2.shape == (n, 8, 47) and t1.is_cuda
+    assert rel_state_err(t1.cpu().numpy(), r1.numpy(), 4) <= 1e-5 and rel_state_err(t2.cpu().numpy(), r2.numpy(), 4) <= 1e-5
+    assert (c2.cpu().double() - rc2).abs().max() <= 2e-4 * max(1.0, float(rc2.abs().max()))
+    with torch.no_grad():
+        one = nb.OCflow_shock(x[:3].cuda(), net, prob, nt, [0.1, shock[:1]], "rk4", meta["alph"])  # a [1,d] shock row broadcasts
+    assert one[2].shape == (3, 8, 47)
