@@ -587,7 +587,7 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
         else if (!strcmp(e, "tile")) use_vec = false;
     }
     if (std::max(ph->m, ph->d + 4) > 1024) use_vec = false;
-    // tensor-core path (noc_tc_quad.cu) for the shapes it is written for; NOC_TC=0 turns it off, NOC_FORCE_PATH=tc forces it
+    // tensor-core path (noc_tc_rollout.cuh) for the shapes it is written for; NOC_TC=0 turns it off, NOC_FORCE_PATH=tc forces it
     bool use_tc = false;
     const int tc_shape = std::is_same<real, float>::value ? tc_shape_id(ph, pb) : -1;
     if (tc_shape >= 0) {                                  // on by default; NOC_TC=0 keeps the FMA kernels
