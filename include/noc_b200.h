@@ -23,6 +23,9 @@
  *     (src/Phi.py:77-87, 32-36): no re-layout is required of the caller
  *   - re-entrant and stream-ordered: work is enqueued on `stream`; only the *_host variants and
  *     noc_measure_* synchronise
+ *   - scratch is allocated stream-ordered (cudaMallocAsync) from the device's default memory pool; on first use of a device
+ *     the library raises that pool's release threshold to 1 GiB (env NOC_POOL_KEEP_MB overrides) so that freed scratch is
+ *     reused instead of being returned to the driver at every synchronisation — a process-wide setting of that device's pool
  *   - there is no CPU implementation behind any of these: without a CUDA device they fail with
  *     NOC_ERR_CUDA
  */

@@ -12,6 +12,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -304,26 +305,40 @@ static size_t plan_smem(SmemPlan& sp, const CfgInfo& ci, const PhiPack<real>& P,
     return best_bytes;
 }
 
-static int g_smem_optin = -1, g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;
+// Device facts, cached per device index (a process may drive several GPUs), filled under a mutex.
+struct DevFacts { int smem_optin = -1, sm_count = 0, cc_major = 0, cc_minor = 0; };
+static DevFacts g_facts[64];
+static std::mutex g_facts_mu;
+static thread_local int g_smem_optin = -1, g_sm_count = 0, g_cc_major = 0, g_cc_minor = 0;     // facts of the calling thread's current device
 int device_facts();
 int sm_count() { device_facts(); return g_sm_count; }
 int device_facts() {
-    if (g_smem_optin >= 0) return NOC_OK;
     int dev = 0;
     NOC_CUDA(cudaGetDevice(&dev));
-    int v = 0;
-    NOC_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-    NOC_CUDA(cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev));
-    NOC_CUDA(cudaDeviceGetAttribute(&g_cc_major, cudaDevAttrComputeCapabilityMajor, dev));
-    NOC_CUDA(cudaDeviceGetAttribute(&g_cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
-    // scratch comes from the stream-ordered pool on every call: keep freed blocks cached instead of returning them
-    // to the driver at each synchronisation (the default threshold of 0 re-allocates 100 MB inputs every call)
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-        unsigned long long keep = ~0ull;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    if (dev < 0 || dev >= 64) return fail(NOC_ERR_ARG, "device index %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_facts_mu);
+    DevFacts& f = g_facts[dev];
+    if (f.smem_optin < 0) {
+        int v = 0;
+        NOC_CUDA(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        NOC_CUDA(cudaDeviceGetAttribute(&f.sm_count, cudaDevAttrMultiProcessorCount, dev));
+        NOC_CUDA(cudaDeviceGetAttribute(&f.cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+        NOC_CUDA(cudaDeviceGetAttribute(&f.cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+        // Scratch comes from the device's default stream-ordered pool on every call.  With the default release threshold (0)
+        // every synchronisation returns it to the driver and 100 MB inputs are re-allocated per call; keep up to 1 GiB cached
+        // (bounded: the pool is shared with the host application and sits outside PyTorch's caching allocator).
+        // NOC_POOL_KEEP_MB overrides; documented in include/noc_b200.h.
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            unsigned long long keep = 1ull << 30;
+            if (const char* e = getenv("NOC_POOL_KEEP_MB")) keep = (unsigned long long)atoll(e) << 20;
+            unsigned long long cur = 0;
+            if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) != cudaSuccess || cur < keep)
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        f.smem_optin = v;
     }
-    g_smem_optin = v;
+    g_smem_optin = f.smem_optin; g_sm_count = f.sm_count; g_cc_major = f.cc_major; g_cc_minor = f.cc_minor;
     return NOC_OK;
 }
 
@@ -674,14 +689,29 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
     const long long rows_per = (((n + nchunk - 1) / nchunk + 127) / 128) * 128;
     if (mode == NOC_MODE_MEAN) ob = sizeof(double) * 8 * (size_t)nchunk;
     void *xd = nullptr, *od = nullptr, *zd = nullptr, *cd = nullptr;
-    NOC_CUDA(cudaMallocAsync(&xd, xb, st));
-    if (ob) NOC_CUDA(cudaMallocAsync(&od, ob, st));
-    if (zb) NOC_CUDA(cudaMallocAsync(&zd, zb, st));
-    if (cb) NOC_CUDA(cudaMallocAsync(&cd, cb, st));
+    auto release = [&] {                                   // one cleanup path: every exit frees what was allocated
+        if (xd) cudaFreeAsync(xd, st);
+        if (od) cudaFreeAsync(od, st);
+        if (zd) cudaFreeAsync(zd, st);
+        if (cd) cudaFreeAsync(cd, st);
+        xd = od = zd = cd = nullptr;
+    };
+    {
+        cudaError_t e = cudaMallocAsync(&xd, xb, st);
+        if (e == cudaSuccess && ob) e = cudaMallocAsync(&od, ob, st);
+        if (e == cudaSuccess && zb) e = cudaMallocAsync(&zd, zb, st);
+        if (e == cudaSuccess && cb) e = cudaMallocAsync(&cd, cb, st);
+        if (e != cudaSuccess) {
+            release();
+            (void)cudaGetLastError();
+            return fail(NOC_ERR_NOMEM, "device buffers for the host entry point (%zu + %zu + %zu + %zu B): %s", xb, ob, zb, cb, cudaGetErrorString(e));
+        }
+    }
     int rc = NOC_OK;
     double sums_h[64 * 8];
     if (nchunk == 1) {
-        NOC_CUDA(cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, st));
+        cudaError_t e = cudaMemcpyAsync(xd, xh, xb, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) { release(); return fail(NOC_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(e)); }
         rc = ocflow_impl<real>(ph, pb, xd, n, stage_times, t0, t1, nt, stepper, alph, mode, od, zd, cd, st, dtype);
     } else {
         // streams: `cs` copies; chunks alternate between `st` and `as` so that a chunk's last, partly filled wave of tiles
@@ -727,10 +757,7 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
         if (e == cudaSuccess && cb && c_h) e = cudaMemcpyAsync(c_h, cd, cb, cudaMemcpyDeviceToHost, st);
         if (e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
     }
-    cudaFreeAsync(xd, st);
-    if (od) cudaFreeAsync(od, st);
-    if (zd) cudaFreeAsync(zd, st);
-    if (cd) cudaFreeAsync(cd, st);
+    release();
     cudaError_t e = cudaStreamSynchronize(st);
     if (rc == NOC_OK && e != cudaSuccess) rc = fail(NOC_ERR_CUDA, "rollout failed: %s", cudaGetErrorString(e));
     if (rc == NOC_OK && mode == NOC_MODE_MEAN && out_h) {          // chunk partials -> [sums, count], fixed order

@@ -698,8 +698,22 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
         }
     }
     const int by_regs = regs_sm / (align_up(std::max(fa.numRegs, 1), 8) * SH::NT);
-    const int by_smem = (int)(smem_sm / (smem + fa.sharedSizeBytes + 1024));
     const int tmem_per_cta = A.tmem_cols + ((SH::PARK && A.park_col < 0) ? 32 : 0);
+    // A CTA that cannot get its TMEM columns blocks inside tcgen05.alloc, and PARK shapes allocate in two steps: if more CTAs
+    // than 512 / tmem_per_cta ever shared an SM (this launch's, or another stream's launch of the same kernel) they could each
+    // hold the first block and wait forever for the second.  Make it structurally impossible: shared memory is the per-SM
+    // resource every co-resident CTA needs, so request enough of it that at most 512 / tmem_per_cta CTAs fit.
+    size_t smem_req = smem;
+    {
+        const int cap = std::max(1, 512 / tmem_per_cta);
+        if ((int)(smem_sm / (smem_req + fa.sharedSizeBytes + 1024)) > cap) {
+            smem_req = (size_t)smem_sm / cap - fa.sharedSizeBytes - 1024;
+            smem_req = std::min(smem_req, (size_t)smem_limit) & ~(size_t)15;
+            while ((int)(smem_sm / (smem_req + fa.sharedSizeBytes + 1024)) > cap && smem_req + 16 <= (size_t)smem_limit) smem_req += 16;
+            NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req));
+        }
+    }
+    const int by_smem = (int)(smem_sm / (smem_req + fa.sharedSizeBytes + 1024));
     int per_sm = std::min(std::min(by_regs, by_smem), 512 / tmem_per_cta);
     if (getenv("NOC_DEBUG"))
         fprintf(stderr, "[noc] tc occupancy: api=%d regs=%d (->%d) smem->%d tmem->%d\n", occ_api, fa.numRegs, by_regs, by_smem, 512 / tmem_per_cta);
@@ -722,7 +736,7 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
         if (cudaMallocAsync((void**)&stage, bytes, st) != cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
     }
     A.stage = stage;
-    kern<<<grid, SH::NT, smem, st>>>(A);
+    kern<<<grid, SH::NT, smem_req, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
     if (stage) {
