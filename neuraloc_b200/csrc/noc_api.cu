@@ -596,6 +596,7 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     if (rc) return rc;
     long long vec_max = 256;
     if (const char* e = getenv("NOC_VEC_MAX")) vec_max = atoll(e);
+    if (std::is_same<real, float>::value && ts_shape_ok(ph, pb) && !getenv("NOC_VEC_MAX")) vec_max = 64;   // beyond that the CTA-pair kernel is faster
     bool use_vec = n <= vec_max;
     if (const char* e = getenv("NOC_FORCE_PATH")) {
         if (!strcmp(e, "vec")) use_vec = true;
@@ -650,11 +651,15 @@ static int ocflow_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x,
     else if (use_tc)
         rc = tc_launch(tc_shape, ph->m, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, tab.data(), nt, stepper, mode, alph, t1,
                        (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
-    else if (use_vec)
+    else if (use_vec) {
+        bool took = false;
+        rc = lat_rollout<real>(&took, ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode,
+                               alph, t1, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c, g_smem_optin, st);
+        if (rc == NOC_OK && !took)
         rc = vec_rollout<real>(ph->d, ph->m, ph->nTh, ph->r, (double)A.phi.h, R, A.prob, (const real*)x, n, dtab, nt, stepper, mode, alph,
                                t1, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr, A.out_a, A.out_b, A.out_c,
                                g_smem_optin, st);
-    else
+    } else
         rc = dispatch<real>(cfg_id, A, &R, KMODE_ROLLOUT, smem, st, (mode == NOC_MODE_MEAN) ? (double*)out_costs : nullptr);
     cudaError_t e = cudaFreeAsync(dtab, st);
     if (rc) return rc;

@@ -43,6 +43,13 @@ int vec_rollout(int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw,
                 const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
                 real* out_nomean, real* zFull, real* ctrlFull, int smem_limit, cudaStream_t st);
 
+// deployment-latency path (noc_lat.cu): one thread-block cluster per sample, weights resident in distributed shared memory.
+// *took = false: not applicable (nTh != 2, slices do not fit, clusters unavailable) -> use vec_rollout.
+template <typename real>
+int lat_rollout(bool* took, int d, int m, int nTh, int r, double h, const PhiRaw<real>& raw, const ProbPack& pr, const real* x, long long n,
+                const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
+                real* out_nomean, real* zFull, real* ctrlFull, int smem_limit, cudaStream_t st);
+
 // one translation unit per configuration (noc_inst.cu with -DNOC_CFG_ID=k) defines these
 #define NOC_DECL_LAUNCH(ID, REAL) \
     int launch_cfg_##ID(const RolloutArgs<REAL>& A, const PhiRaw<REAL>* raw, int kmode, size_t smem, cudaStream_t st, double* out_sums);

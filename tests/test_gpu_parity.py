@@ -16,11 +16,14 @@ pytestmark = pytest.mark.gpu
 TOL = {"f32": dict(state=1e-5, cost=1e-4, floor=2e-4, ctrl=2e-4), "f64": dict(state=1e-11, cost=1e-9, floor=1e-10, ctrl=1e-9)}
 
 
-@pytest.fixture(autouse=True, params=["tile", "vec"])
+@pytest.fixture(autouse=True, params=["tile", "vec", "vec1"])
 def path(request, monkeypatch):
-    """Every rollout test runs through both kernels: the sample-tile kernel (large batches) and the one-CTA-per-sample
-    kernel (small batches / deployment latency).  NOC_FORCE_PATH pins the choice the host would make by batch size."""
-    monkeypatch.setenv("NOC_FORCE_PATH", request.param)
+    """Every rollout test runs through the sample-tile kernel (large batches) and through both small-batch kernels: the cluster
+    latency kernel (noc_lat.cu: "vec", the default for small batches) and the one-CTA-per-sample kernel (noc_vec.cu: "vec1",
+    NOC_NO_LAT=1; also the fallback for nTh > 2).  NOC_FORCE_PATH pins the choice the host would make by batch size."""
+    monkeypatch.setenv("NOC_FORCE_PATH", "vec" if request.param == "vec1" else request.param)
+    if request.param == "vec1":
+        monkeypatch.setenv("NOC_NO_LAT", "1")
     return request.param
 
 
@@ -110,7 +113,11 @@ def test_rk1_and_unknown_stepper_golden(nb, name, tag):
     d = xinit.shape[1]
     xb = torch.from_numpy(c["xb"]).to(DT[tag]).cuda()
     got = _three_modes(nb, xb[:4], net, prob, [0.0, 1.0], 8, "rk1", meta["alph"])
-    _compare(tag, d, got, (c["rk1_mean_" + tag], None, c["rk1_z_" + tag], c["rk1_ctrl_" + tag]), name + " rk1")
+    # Euler with 8 steps on the adversarial rows is ill-conditioned in fp32 (the reference's own fp32 run is up to 1.05e-5 from
+    # its fp64 run on swap12): gate against the fp64 trajectories at 1e-5 or twice the reference's own fp32 distance
+    ref_err = rel_state_err(c["rk1_z_f32"], c["rk1_z_f64"], d)
+    _compare(tag, d, got, (c["rk1_mean_f64"], None, c["rk1_z_f64"], c["rk1_ctrl_f64"]), name + " rk1",
+             state_tol=max(TOL[tag]["state"], 2 * ref_err) if tag == "f32" else None)
     got = _three_modes(nb, xb[:2], net, prob, [0.0, 1.0], 3, "none", meta["alph"])
     _compare(tag, d, got, (c["nostep_mean_" + tag], None, c["nostep_z_" + tag], c["nostep_ctrl_" + tag]), name + " no stepper")
 
