@@ -155,21 +155,24 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
         if (CL) { cg::this_cluster().sync(); } else { __syncthreads(); }
     };
     sync_all();
-    // exchange: my `cnt` values tmp[0..cnt) become elements [rank*cnt, rank*cnt + cnt) of `dst` in EVERY CTA of the cluster
-    auto all_gather = [&](real* dst, int cnt) {
-        __syncthreads();
+    // exchange: the thread that holds output `e` of my slice stores it as element rank*cnt + e of `dst` in EVERY CTA of the
+    // cluster (distributed-shared-memory stores), then one cluster barrier publishes the vector (publish_sync)
+    // (single CTA: stored directly; cluster: staged in `tmp` and distributed by all 256 threads, two remote stores each,
+    // which measured faster than 16 serial remote stores by the producing thread)
+    auto put_all = [&](real* dst, int cnt, int e, real v, int slot = 0) {
+        if (CL) tmp[slot * cnt + e] = v; else dst[rank * cnt + e] = v;
+    };
+    auto publish_sync = [&](real* dst, int cnt, real* dst2 = nullptr) {
         if (CL) {
+            __syncthreads();
             cg::cluster_group cl = cg::this_cluster();
             for (int i = tid; i < cnt * NC; i += NT) {
                 const int r = i / cnt, e = i % cnt;
-                real* remote = cl.map_shared_rank(dst, r);
-                remote[rank * cnt + e] = tmp[e];
+                cl.map_shared_rank(dst, r)[rank * cnt + e] = tmp[e];
+                if (dst2) cl.map_shared_rank(dst2, r)[rank * cnt + e] = tmp[cnt + e];
             }
             cl.sync();
-        } else {
-            for (int e = tid; e < cnt; e += NT) dst[e] = tmp[e];
-            __syncthreads();
-        }
+        } else __syncthreads();
     };
     // threads per output for the m-wide and the D-wide contractions
     int TPOm = 1; while (TPOm * 2 * mc <= NT && TPOm < 32) TPOm *= 2;
@@ -181,15 +184,15 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
     auto chain = [&](bool terminal) -> real {
         {                                                   // opening layer: o = K0 s + b0 (own units)
             const real pre = gemv_split<real>(W1 + omc * KD, s, KD, TPOm, pm) + b0[omc];
-            if (om < mc && pm == 0) { real av, tv; act_tanh(pre, av, tv); tmp[om] = av; t0b[om] = tv; }
+            if (om < mc && pm == 0) { real av, tv; act_tanh(pre, av, tv); put_all(ub, mc, om, av); t0b[om] = tv; }
         }
-        all_gather(ub, mc);                                 // u0, all units
+        publish_sync(ub, mc);                               // u0, all units
         real part = real(0);
         {                                                   // a1 = K1 u0 + b1 -> y = tanh(a1) w
             const real pre = gemv_split<real>(K1f + omc * Km, ub, Km, TPOm, pm) + b1[omc];
             if (om < mc && pm == 0) {
-                if (terminal) { real av, tv; act_tanh(pre, av, tv); part = wv[om] * (ub[rank * mc + om] + A.h * av); tmp[om] = tv * wv[om]; }
-                else tmp[om] = tanh_only(pre) * wv[om];
+                if (terminal) { real av, tv; act_tanh(pre, av, tv); part = wv[om] * (ub[rank * mc + om] + A.h * av); put_all(yb, mc, om, tv * wv[om]); }
+                else put_all(yb, mc, om, tanh_only(pre) * wv[om]);
             }
         }
         real phiN = real(0);
@@ -200,37 +203,26 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
                 if (tid < NC) { real* remote = cl.map_shared_rank(phib, tid); remote[rank] = mine; }
             } else if (tid == 0) phib[0] = mine;
         }
-        all_gather(yb, mc);                                 // y, all units (the barrier also publishes phib)
+        publish_sync(yb, mc);                               // y, all units (the barrier also publishes phib)
         if (terminal) { for (int r = 0; r < NC; ++r) phiN += phib[r]; }
         {                                                   // z1 = w + h K1' y -> v = tanh(o) z1 (own units)
             const real acc = gemv_split<real>(K1r + omc * Km, yb, Km, TPOm, pm);
-            if (om < mc && pm == 0) tmp[om] = t0b[om] * (wv[om] + A.h * acc);
+            if (om < mc && pm == 0) put_all(vb, mc, om, t0b[om] * (wv[om] + A.h * acc));
         }
-        all_gather(vb, mc);                                 // v, all units
+        publish_sync(vb, mc);                               // v, all units
         {                                                   // grad = A'A s + K0' v + c_w (own components)
             const real q = gemv_split<real>(sym + odc * KD, s, KD, TPOd, pd);
             const real k0v = gemv_split<real>(W4 + odc * Km, vb, Km, TPOd, pd);
-            if (od < dc && pd == 0) { tmp[od] = (q + k0v) + cw[od]; tmp[dc + od] = q; }
+            if (od < dc && pd == 0) { put_all(g, dc, od, (q + k0v) + cw[od]); put_all(qv, dc, od, q, 1); }
         }
-        __syncthreads();
-        if (CL) {                                           // g and q = A'A s, all components, in every CTA
-            cg::cluster_group cl = cg::this_cluster();
-            for (int i = tid; i < dc * NC; i += NT) {
-                const int r = i / dc, e = i % dc;
-                cl.map_shared_rank(g, r)[rank * dc + e] = tmp[e];
-                cl.map_shared_rank(qv, r)[rank * dc + e] = tmp[dc + e];
-            }
-            cl.sync();
-        } else {
-            for (int e = tid; e < dc; e += NT) { g[e] = tmp[e]; qv[e] = tmp[dc + e]; }
-            __syncthreads();
-        }
+        publish_sync(g, dc, qv);                            // g and q = A'A s, all components, in every CTA
         return phiN;
     };
 
     // L, |Phi_t - H|, Q, W -> sc[0..3] from x = s[:d], p = g[:d] (calcLHQW of the three problem classes); as in noc_vec.cu
     const bool needQ = (pr.obstacle != 0) && (pr.kind == 0 || pr.alph_Q > 0.0), hasW = (pr.alph_W != 0.0), posQ = (pr.alph_Q > 0.0);
     const real f_alphQ = real(pr.alph_Q), f_alphW = real(pr.alph_W), f_cut = real(pr.cutW), f_c2 = real(2 * pr.r * pr.r);
+    const real f_guard = f_cut * f_cut * real(1.0001);
     const real f_mass = real(pr.mass), f_grav = real(pr.grav), f_uscale = real(-1.0 / (2.0 * pr.mass)), f_cutq = real(2 * pr.r);
     const int p_kind = pr.kind, Ag = pr.nAgents, dim = pr.agentDim, nctrl = pr.nctrl;
     auto problem = [&]() {
@@ -279,10 +271,12 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
                 for (int j = i + 1 + tid % TPR; j < Ag; j += TPR) {
                     real d2 = real(0);
                     for (int c = 0; c < dim; ++c) { real df = s[i * dim + c] - s[j * dim + c]; d2 = r_fma(df, df, d2); }
-                    real dd = r_sqrt(d2);
-                    if (dd < f_cut) {
-                        real e = r_exp(-(dd * dd) / f_c2);
-                        if (Ag == 2 || e != real(1)) wm += e;   // the "== 1" rule applies to the A > 2 branch only
+                    if (d2 < f_guard) {                         // (widened squared cut-off first: the exact test needs a sqrt)
+                        real dd = r_sqrt(d2);
+                        if (dd < f_cut) {
+                            real e = r_exp(-(dd * dd) / f_c2);
+                            if (Ag == 2 || e != real(1)) wm += e;   // the "== 1" rule applies to the A > 2 branch only
+                        }
                     }
                 }
         }
