@@ -8,8 +8,10 @@
 //     tree), 256 threads per CTA;
 //   * the hidden units (and the gradient components) are partitioned over the NC CTAs of a cluster; each CTA keeps ITS rows of
 //     K0, K1, K1', K0', A'A in shared memory for the whole rollout (swarm50: 16 CTAs x 186 KB), so nothing is re-read from L2;
-//   * after each contraction the CTAs exchange their slice of the result by distributed-shared-memory stores into every
-//     peer's copy of the vector (an all-gather of m or D floats) and one cluster barrier; NC = 1 (all nets up to m = 128)
+//   * after each contraction the CTAs exchange their slice of the result: every CTA bulk-copies its slice into every peer's
+//     copy of the vector through distributed shared memory (cp.async.bulk shared::cta -> shared::cluster, 16 copies issued by
+//     16 threads) and each peer's mbarrier counts the bytes -- an all-gather of m or D floats without a cluster-wide barrier
+//     (barrier.cluster with its MEMBAR was 35 % of the stall samples of the first version); NC = 1 (all nets up to m = 128)
 //     degenerates to __syncthreads();
 //   * the per-sample work (calcLHQW, RK update, terminal block) is done redundantly by every CTA of the cluster, so no further
 //     exchange is needed; rank 0 writes the outputs.
@@ -20,6 +22,7 @@
 #include <cstdlib>
 
 #include "noc_launch.cuh"
+#include "noc_tc.cuh"
 
 namespace cg = cooperative_groups;
 
@@ -141,6 +144,9 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
     real* t0b = sm + A.o_t;    real* g = sm + A.o_g;     real* qv = sm + A.o_q;    real* sc = sm + A.o_sc;
     real* red = sm + A.o_red;  real* qx = sm + A.o_qx;   real* tmp = sm + A.o_tmp; real* phib = sm + A.o_phi;
     real* z0 = sm + A.o_z0;    real* za = sm + A.o_za;   real* wsl = sm + A.o_w;
+    __shared__ __align__(8) unsigned long long gbar[4];   // one mbarrier per exchanged vector (u0, y, v, grad)
+    int gphase = 0;
+    if (CL && tid == 0) { for (int k = 0; k < 4; ++k) mbar_init(smem_u32(&gbar[k]), 1); fence_mbar_init_cluster(); }
     // my weight slice -> shared memory (once), vectors zeroed (the padded tails are read by gemv_split)
     {
         const real* src = A.blob + (size_t)rank * A.slice_len;
@@ -157,21 +163,23 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
     sync_all();
     // exchange: the thread that holds output `e` of my slice stores it as element rank*cnt + e of `dst` in EVERY CTA of the
     // cluster (distributed-shared-memory stores), then one cluster barrier publishes the vector (publish_sync)
-    // (single CTA: stored directly; cluster: staged in `tmp` and distributed by all 256 threads, two remote stores each,
-    // which measured faster than 16 serial remote stores by the producing thread)
-    auto put_all = [&](real* dst, int cnt, int e, real v, int slot = 0) {
-        if (CL) tmp[slot * cnt + e] = v; else dst[rank * cnt + e] = v;
+    // (single CTA: stored directly; cluster: staged in this exchange's own `tmp` slot and bulk-copied to every peer)
+    const int tslot = A.o_phi - A.o_tmp >= 0 ? (A.o_phi - A.o_tmp) / 4 : 0;       // elements per tmp slot
+    auto put_all = [&](int k, real* dst, int cnt, int e, real v, int second = 0) {
+        if (CL) tmp[k * tslot + second * cnt + e] = v; else dst[rank * cnt + e] = v;
     };
-    auto publish_sync = [&](real* dst, int cnt, real* dst2 = nullptr) {
+    auto publish_sync = [&](int k, real* dst, int cnt, real* dst2 = nullptr) {
         if (CL) {
+            fence_async_smem();                          // my tmp writes -> visible to the bulk-copy engine
             __syncthreads();
-            cg::cluster_group cl = cg::this_cluster();
-            for (int i = tid; i < cnt * NC; i += NT) {
-                const int r = i / cnt, e = i % cnt;
-                cl.map_shared_rank(dst, r)[rank * cnt + e] = tmp[e];
-                if (dst2) cl.map_shared_rank(dst2, r)[rank * cnt + e] = tmp[cnt + e];
+            const unsigned bytes = (unsigned)(cnt * sizeof(real));
+            if (tid == 0) mbar_arrive_expect_tx(smem_u32(&gbar[k]), bytes * NC * (dst2 ? 2 : 1));
+            if (tid < NC) {
+                const unsigned peer_bar = mapa_shared(smem_u32(&gbar[k]), tid);
+                dsmem_bulk_copy(mapa_shared(smem_u32(dst + rank * cnt), tid), smem_u32(tmp + k * tslot), bytes, peer_bar);
+                if (dst2) dsmem_bulk_copy(mapa_shared(smem_u32(dst2 + rank * cnt), tid), smem_u32(tmp + k * tslot + cnt), bytes, peer_bar);
             }
-            cl.sync();
+            mbar_wait_cluster(smem_u32(&gbar[k]), gphase, 400 + k);
         } else __syncthreads();
     };
     // threads per output for the m-wide and the D-wide contractions
@@ -184,15 +192,15 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
     auto chain = [&](bool terminal) -> real {
         {                                                   // opening layer: o = K0 s + b0 (own units)
             const real pre = gemv_split<real>(W1 + omc * KD, s, KD, TPOm, pm) + b0[omc];
-            if (om < mc && pm == 0) { real av, tv; act_tanh(pre, av, tv); put_all(ub, mc, om, av); t0b[om] = tv; }
+            if (om < mc && pm == 0) { real av, tv; act_tanh(pre, av, tv); put_all(0, ub, mc, om, av); t0b[om] = tv; }
         }
-        publish_sync(ub, mc);                               // u0, all units
+        publish_sync(0, ub, mc);                               // u0, all units
         real part = real(0);
         {                                                   // a1 = K1 u0 + b1 -> y = tanh(a1) w
             const real pre = gemv_split<real>(K1f + omc * Km, ub, Km, TPOm, pm) + b1[omc];
             if (om < mc && pm == 0) {
-                if (terminal) { real av, tv; act_tanh(pre, av, tv); part = wv[om] * (ub[rank * mc + om] + A.h * av); put_all(yb, mc, om, tv * wv[om]); }
-                else put_all(yb, mc, om, tanh_only(pre) * wv[om]);
+                if (terminal) { real av, tv; act_tanh(pre, av, tv); part = wv[om] * (ub[rank * mc + om] + A.h * av); put_all(1, yb, mc, om, tv * wv[om]); }
+                else put_all(1, yb, mc, om, tanh_only(pre) * wv[om]);
             }
         }
         real phiN = real(0);
@@ -201,21 +209,23 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
             if (CL) {
                 cg::cluster_group cl = cg::this_cluster();
                 if (tid < NC) { real* remote = cl.map_shared_rank(phib, tid); remote[rank] = mine; }
+                cl.sync();                                  // (once per rollout) publishes phib
             } else if (tid == 0) phib[0] = mine;
         }
-        publish_sync(yb, mc);                               // y, all units (the barrier also publishes phib)
+        publish_sync(1, yb, mc);                            // y, all units
         if (terminal) { for (int r = 0; r < NC; ++r) phiN += phib[r]; }
         {                                                   // z1 = w + h K1' y -> v = tanh(o) z1 (own units)
             const real acc = gemv_split<real>(K1r + omc * Km, yb, Km, TPOm, pm);
-            if (om < mc && pm == 0) put_all(vb, mc, om, t0b[om] * (wv[om] + A.h * acc));
+            if (om < mc && pm == 0) put_all(2, vb, mc, om, t0b[om] * (wv[om] + A.h * acc));
         }
-        publish_sync(vb, mc);                               // v, all units
+        publish_sync(2, vb, mc);                               // v, all units
         {                                                   // grad = A'A s + K0' v + c_w (own components)
             const real q = gemv_split<real>(sym + odc * KD, s, KD, TPOd, pd);
             const real k0v = gemv_split<real>(W4 + odc * Km, vb, Km, TPOd, pd);
-            if (od < dc && pd == 0) { put_all(g, dc, od, (q + k0v) + cw[od]); put_all(qv, dc, od, q, 1); }
+            if (od < dc && pd == 0) { put_all(3, g, dc, od, (q + k0v) + cw[od]); put_all(3, qv, dc, od, q, 1); }
         }
-        publish_sync(g, dc, qv);                            // g and q = A'A s, all components, in every CTA
+        publish_sync(3, g, dc, qv);
+        gphase ^= 1;                            // g and q = A'A s, all components, in every CTA
         return phiN;
     };
 
@@ -265,10 +275,19 @@ __global__ void __launch_bounds__(256, 1) rollout_lat_kernel(const LatArgs<real>
         if (needQ)
             for (int a = tid; a < Ag; a += NT) qm += terrain_agent<real>(pr, s[a * dim], s[a * dim + 1], dim == 3 ? s[a * dim + 2] : real(0));
         if (hasW && Ag >= 2) {
-            // pair (i, j > i): row i by thread group, j strided inside the group (no index decoding; at most ceil(A / TPR) pairs each)
-            int TPR = 1; while (TPR * 2 * (Ag - 1) <= NT && TPR < 32) TPR *= 2;
-            for (int i = tid / TPR; i < Ag - 1; i += NT / TPR)
-                for (int j = i + 1 + tid % TPR; j < Ag; j += TPR) {
+            // pairs (i, j > i): thread group `gi` takes the rows gi and A-2-gi (together A pairs: balanced), j strided inside the
+            // group -- no index decoding, at most ceil(A / TPR) pairs per thread
+            const int nfold = Ag / 2;                                 // row pairs (gi, A-2-gi); the middle row of an even count alone
+            int TPR = 1; while (TPR * 2 * nfold <= NT && TPR < 32) TPR *= 2;
+            for (int gi = tid / TPR; gi < nfold; gi += NT / TPR)
+                for (int t = tid % TPR; t < Ag; t += TPR) {
+                    // the t-th pair of the folded row: first the A-1-gi pairs of row gi, then the gi+1 pairs of row A-2-gi
+                    int i, j;
+                    if (t < Ag - 1 - gi) { i = gi; j = gi + 1 + t; }
+                    else {
+                        if (2 * gi == Ag - 2) continue;               // the middle row is its own partner: counted once
+                        i = Ag - 2 - gi; j = i + 1 + (t - (Ag - 1 - gi));
+                    }
                     real d2 = real(0);
                     for (int c = 0; c < dim; ++c) { real df = s[i * dim + c] - s[j * dim + c]; d2 = r_fma(df, df, d2); }
                     if (d2 < f_guard) {                         // (widened squared cut-off first: the exact test needs a sqrt)
@@ -426,7 +445,8 @@ int lat_rollout(bool* took, int d, int m, int nTh, int r, double h, const PhiRaw
     int NC = 0;
     size_t smem = 0;
     auto plan = [&](int nc) -> bool {                          // slice + vector layout for a cluster of nc CTAs; true if it fits
-        const int mc = ceil_div(m, nc), dc = ceil_div(D, nc);
+        const int V = 16 / elt;                               // slices are bulk-copied: multiples of 16 bytes
+        const int mc = (nc > 1) ? align_up(ceil_div(m, nc), V) : m, dc = (nc > 1) ? align_up(ceil_div(D, nc), V) : D;
         if (mc > 256 || 2 * dc > 256) return false;
         int off = 0;
         auto take = [&](int cnt) { int o = off; off += align_up(cnt, 8); return o; };
@@ -439,7 +459,7 @@ int lat_rollout(bool* took, int d, int m, int nTh, int r, double h, const PhiRaw
         A.o_s = stake(std::max(A.Kp_D, dfull)); A.o_u = stake(std::max(A.Kp_m, mfull)); A.o_y = stake(std::max(A.Kp_m, mfull));
         A.o_v = stake(std::max(A.Kp_m, mfull)); A.o_t = stake(mc); A.o_g = stake(std::max(A.Kp_D, dfull)); A.o_q = stake(std::max(A.Kp_D, dfull));
         A.o_z0 = stake(d + 4); A.o_za = stake(d + 4); A.o_sc = stake(8); A.o_red = stake(32); A.o_qx = stake(5 * std::max(1, pr.nAgents));
-        A.o_tmp = stake(std::max(mc, 2 * dc)); A.o_phi = stake(2 * 16); A.o_w = so;
+        A.o_tmp = stake(4 * align_up(std::max(mc, 2 * dc), 8)); A.o_phi = stake(2 * 16); A.o_w = so;      // four exchange slots
         smem = (size_t)(so + A.slice_len) * elt;
         if (smem > (size_t)smem_limit) return false;
         NC = nc; A.mc = mc; A.dc = dc;

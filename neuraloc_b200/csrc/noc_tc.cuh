@@ -213,6 +213,12 @@ __device__ __forceinline__ void tma2_load_2d(unsigned dst_smem, const void* tmap
     asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  :: "r"(dst_smem), "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(mbar_cluster_addr), "r"(c0), "r"(c1) : "memory");
 }
+// bulk copy of `bytes` (multiple of 16) from THIS CTA's shared memory into another CTA's of the cluster; the bytes are reported
+// to the mbarrier at `mbar_cluster_addr` (in the destination CTA).  SASS: UBLKCP.
+__device__ __forceinline__ void dsmem_bulk_copy(unsigned dst_cluster_addr, unsigned src_cta_addr, unsigned bytes, unsigned mbar_cluster_addr) {
+    asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(dst_cluster_addr), "r"(src_cta_addr), "r"(bytes), "r"(mbar_cluster_addr) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const void* tmap) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
 }
