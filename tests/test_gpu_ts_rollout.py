@@ -140,3 +140,47 @@ def test_ts_intermediates_staged_equals_direct(nb, monkeypatch):
     assert za.shape == (x.shape[0], d + 4, 4) and ca.shape == (x.shape[0], d, 4)
     assert torch.equal(za, zb) and torch.equal(ca, cb)
     assert torch.equal(za[:, :d, 0], x) and not ca[:, :, 0].any() and not za[:, d:, 0].any()
+
+
+def test_ts_train_mode_and_narrower_net(nb):
+    """prob.train() (boxes inflated by r, Gaussian + 999 terrain, the 3.2 r interaction cut-off: SwarmTraj.py:101-119,140-156) on
+    the adversarial rows, and a random-init network narrower than the kernel's 512 columns (m = 320: zero-padded units), both
+    against the fp64 oracle."""
+    import dataclasses
+    from oracle import ocflow_oracle as orc
+    c = load_cases("swarm50")
+    net, prob, xinit, meta = product_setup("swarm50", torch.float32)
+    P64, D64, _, _ = oracle_setup("swarm50", torch.float64)
+    d = xinit.shape[1]
+    g = torch.Generator().manual_seed(31)
+    xb = torch.cat((torch.from_numpy(c["xb"]).float(), xinit.cpu() + 0.1 * torch.randn(130, d, generator=g)), 0)
+    nt = 40
+    prob.train()
+    Dtr = dataclasses.replace(D64, training=True)
+    with torch.no_grad():
+        zf, cf = nb.OCflow(xb.cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        assert nb._cabi.last_path() == "tensor"
+        Jn, cn = nb.OCflow(xb.cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+        zr, cr = orc.ocflow(xb.double(), P64, Dtr, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+        Jr, csr = orc.ocflow(xb.double(), P64, Dtr, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+    prob.eval()
+    assert rel_state_err(zf.cpu().numpy(), zr.numpy(), d) <= 1e-5
+    got, ref = torch.cat([Jn] + list(cn), 1).double().cpu().numpy(), torch.cat([Jr] + list(csr), 1).numpy()
+    sc = np.maximum(np.abs(ref).max(axis=0, keepdims=True), 1e-30)
+    perr = (np.abs(got - ref) / sc).max(axis=0)
+    assert (perr[[0, 1, 3, 4, 6, 7]] <= 2e-4).all(), "train-mode per-sample costs vs fp64 oracle: %s" % perr
+    assert ref[:, 6].max() > 100.0                              # the +999 terrain of agents inside the inflated boxes is exercised
+    # a narrower random-init net through the same kernel
+    torch.manual_seed(3)
+    net2 = nb.Phi(nTh=2, m=320, d=d, alph=meta["alph"])
+    P2 = orc.params_from_state_dict({k: v.detach().clone() for k, v in net2.state_dict().items()}, torch.float64)
+    net2 = net2.float().cuda()
+    x = xinit.cpu() + 0.1 * torch.randn(200, d, generator=g)
+    with torch.no_grad():
+        z2, _ = nb.OCflow(x.cuda(), net2, prob, [0.0, 1.0], 20, "rk4", meta["alph"], intermediates=True)
+        assert nb._cabi.last_path() == "tensor"
+        m2 = mean_vec(nb.OCflow(x.cuda(), net2, prob, [0.0, 1.0], 20, "rk4", meta["alph"]))
+        zr2, _ = orc.ocflow(x.double(), P2, D64, [0.0, 1.0], 20, "rk4", meta["alph"], intermediates=True)
+        mr2 = mean_vec(orc.ocflow(x.double(), P2, D64, [0.0, 1.0], 20, "rk4", meta["alph"]))
+    assert rel_state_err(z2.cpu().numpy(), zr2.numpy(), d) <= 1e-5
+    check_costs(m2[:6], mr2[:6], 1e-4, 0.0, "m = 320 random-init net through the streamed kernel")
