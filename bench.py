@@ -77,7 +77,7 @@ def dram_bytes_per_sample(workload, path):
 
 def tensor_flops_per_sample_step(workload, d, m):
     """16-bit tensor-core flops the tcgen05 kernels EXECUTE per sample-step, and what they are.
-    noc_tc_rollout.cuh (m <= 128): 4 evaluations x 6 split products (bf16 x 3) x 2 flops x the padded GEMM volumes
+    noc_tc_rollout.cuh (m <= 128): 4 evaluations x 3 split products (fp16 x 2) x 2 flops x the padded GEMM volumes
     KS*mp + 2*mp*mp + mp*KS + KS*KS (KS = d+2 rounded up to 16; mp = m padded to 64 for the quadcopter shape, 16 otherwise).
     noc_ts_rollout.cuh (swarm50): 4 evaluations x 3 split products (fp16 x 2) x 2 flops x (2*KS*512 + 2*512*512 + KS*KS), KS = 160."""
     if d == 150:
@@ -86,7 +86,7 @@ def tensor_flops_per_sample_step(workload, d, m):
     ks = -(-(d + 2) // 16) * 16
     pad = 64 if workload == "singlequad" else 16
     mp = -(-m // pad) * pad
-    return 4 * 6 * 2 * (ks * mp + 2 * mp * mp + mp * ks + ks * ks), "rollout_tc_kernel (tcgen05, bf16 x 3 split: 6 MMAs per fp32 product)"
+    return 4 * 3 * 2 * (ks * mp + 2 * mp * mp + mp * ks + ks * ks), "rollout_tc_kernel (tcgen05, fp16 x 2 split: 3 MMAs per fp32 product)"
 
 
 def flops_per_sample_step(d, m, nTh, r):

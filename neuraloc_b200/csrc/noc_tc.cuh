@@ -227,13 +227,16 @@ __device__ __forceinline__ void tmem_ld8_issue(unsigned taddr, unsigned (&r)[8])
                  : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr) : "memory");
 }
 // fp32 pair -> packed fp16x2 "hi" and the packed fp16x2 residual "lo": v = hi + lo to ~2^-23 |v| (fp16 has 11 significant
-// bits; the residual of a round-to-nearest fp16 is exactly representable in fp32 and again rounded to 11 bits)
+// bits; the residual of a round-to-nearest fp16 is exactly representable in fp32 and again rounded to 11 bits).
+// Four instructions per pair: F2FP, two mixed-precision FHFMA (residual = hi * -1 + v, reading the fp16 halves in place:
+// PTX fma.rn.f32.f16, sm_100+), F2FP.
 __device__ __forceinline__ void split2_f16(float a, float b, unsigned& hi, unsigned& lo) {
     unsigned h;
     asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(b), "f"(a));          // low half = a, high half = b
-    float ha, hb;
-    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n" : "=f"(ha), "=f"(hb) : "r"(h));
-    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(b - hb), "f"(a - ha));
+    float ra, rb;
+    asm("{\n\t.reg .b16 l, u, m1;\n\tmov.b32 {l, u}, %2;\n\tmov.b16 m1, 0xBC00;\n\t"
+        "fma.rn.f32.f16 %0, l, m1, %3;\n\tfma.rn.f32.f16 %1, u, m1, %4;\n\t}\n" : "=f"(ra), "=f"(rb) : "r"(h), "f"(a), "f"(b));
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(rb), "f"(ra));
     hi = h;
 }
 

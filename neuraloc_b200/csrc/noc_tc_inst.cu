@@ -18,7 +18,7 @@
 #define NOC_TC_CH1 16
 #endif
 #ifndef NOC_TC_MINB1
-#define NOC_TC_MINB1 4
+#define NOC_TC_MINB1 5
 #endif
 
 namespace noc {

@@ -11,14 +11,17 @@
 //     GEMM-2  A1 [128 x m]  = U0 [128 x m] . K1'      B = K1 read K-major
 //     GEMM-3  Z1 [128 x m]  = Y  [128 x m] . K1       B = the SAME K1 buffer read MN-major
 //     GEMM-4  G  [128 x KS] = V  [128 x m] . K0b (MN-major view of the GEMM-1 buffer)  +  S . symb'  (A'A and c_w)
-// Accumulators live in TMEM (fp32); tanh(o) is parked in TMEM between GEMM-1 and GEMM-3.
+// The accumulator lives in TMEM (fp32); tanh(o) is parked in TMEM between GEMM-1 and GEMM-3.
 //
-// Precision: every fp32 operand is split into three bf16 terms (hi, mid, lo) and each logical product is six MMAs
-// (hh, hm, mh, hl, mm, lh; the dropped terms are O(2^-24)), because a single bf16 / tf32 pass breaks the 1e-5
-// per-step-state tolerance.  The hh products accumulate in one TMEM accumulator and the five correction
-// products in another (the tensor core truncates on every fp32 add; the small terms keep their own, 2^-8 smaller, error);
-// the epilogue adds the two in round-to-nearest fp32.  Measured on the B200: as close to the fp64 reference as the
-// fp32 FMA kernels and as torch's own fp32 (scripts/accuracy_probe.py).
+// Precision: every fp32 operand is split into two fp16 terms (hi + lo, 22 significant bits) and each logical product is three
+// MMAs (hi.hi, hi.lo, lo.hi; the dropped lo.lo term is O(2^-22)), because a single bf16 / tf32 pass breaks the 1e-5
+// per-step-state tolerance.  fp16's narrow exponent is handled with per-matrix power-of-two scales computed at
+// set-up (largest weight of a matrix -> [2^13, 2^14), so that the lo plane stays in the normal range; the Y / V operands
+// carry the scale of w the same way); the reciprocal scales are folded into constants the epilogues apply anyway.  The
+// tensor core's fp32 accumulate rounds toward zero (measured: a mean relative shrink of 1.89e-8 per accumulating MMA,
+// scripts/tc_bias_probe.py, scripts/ts_bias_robust.py); the mean is undone in the same reciprocal scales.  (Round 1 used three
+// bf16 planes and six MMAs per product into two accumulators: twice the tensor work, 1.5x the split / store work and twice
+// the TMEM loads for the same measured accuracy.)
 //
 // Operands are written by the epilogue threads straight into the canonical no-swizzle UMMA layout (8-row x 16-byte core
 // matrices), one elected lane issues the MMAs, and tcgen05.commit signals an mbarrier all epilogue threads wait on.
@@ -57,6 +60,8 @@ struct TcArgs {
     float* out_a; float* out_b; float* out_c;
     float* stage;                   // intermediates: tile-major staging buffer [tile][step][row][128 samples] (coalesced), or NULL
     int ntiles, tmem_cols;
+    float bias_f;                   // multiplier of the accumulate-bias compensation (1; experiments: NOC_TC_BIAS)
+    float sx;                       // power-of-two scale of the S = [x, t, 1] operand (fp16 range, see the header)
     int park_col;                   // PARK shapes: column of the parked RK accumulator inside the main block, or -1 = own 32-column block
 };
 
@@ -79,67 +84,52 @@ struct TcShape {
     static_assert(KIND != 2 || NA == 1, "one quadcopter");
 };
 
-// fp32 pair -> three packed bf16x2 terms, v ~ hi + mid + lo (exact to ~2^-24 |v|); registers only
-__device__ __forceinline__ unsigned pack_bf16x2(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);          // .x = a (low half), .y = b
-    return *reinterpret_cast<unsigned*>(&v);
-}
-__device__ __forceinline__ float bf_lo(unsigned p) { return __uint_as_float(p << 16); }
-__device__ __forceinline__ float bf_hi(unsigned p) { return __uint_as_float(p & 0xffff0000u); }
-__device__ __forceinline__ void split3x2(float a, float b, unsigned& hi, unsigned& mid, unsigned& lo) {
-    hi = pack_bf16x2(a, b);
-    const float ra = a - bf_lo(hi), rb = b - bf_hi(hi);
-    mid = pack_bf16x2(ra, rb);
-    lo = pack_bf16x2(ra - bf_lo(mid), rb - bf_hi(mid));
-}
-
-// write 8 consecutive K-elements (one 16-byte chunk) of row `row` of an A/B operand, all three split planes
-__device__ __forceinline__ void store_chunk3(unsigned char* base, int plane_bytes, int row, int k0, int K, const float* v) {
-    uint4 h, mi, l;
-    split3x2(v[0], v[1], h.x, mi.x, l.x);
-    split3x2(v[2], v[3], h.y, mi.y, l.y);
-    split3x2(v[4], v[5], h.z, mi.z, l.z);
-    split3x2(v[6], v[7], h.w, mi.w, l.w);
+// write 8 consecutive K-elements (one 16-byte chunk) of row `row` of an A/B operand, both split planes (hi, lo)
+__device__ __forceinline__ void store_chunk2(unsigned char* base, int plane_bytes, int row, int k0, int K, const float* v) {
+    uint4 h, l;
+    split2_f16(v[0], v[1], h.x, l.x);
+    split2_f16(v[2], v[3], h.y, l.y);
+    split2_f16(v[4], v[5], h.z, l.z);
+    split2_f16(v[6], v[7], h.w, l.w);
     const int off = il_off(row, k0, K);
     *reinterpret_cast<uint4*>(base + off) = h;
-    *reinterpret_cast<uint4*>(base + plane_bytes + off) = mi;
-    *reinterpret_cast<uint4*>(base + 2 * plane_bytes + off) = l;
+    *reinterpret_cast<uint4*>(base + plane_bytes + off) = l;
 }
-__device__ __forceinline__ void load_chunk3(const unsigned char* base, int plane_bytes, int row, int k0, int K, float* v) {
+__device__ __forceinline__ void unpack_f16x2(unsigned p, float& a, float& b) {
+    asm("{\n\t.reg .b16 l, u;\n\tmov.b32 {l, u}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, u;\n\t}\n" : "=f"(a), "=f"(b) : "r"(p));
+}
+__device__ __forceinline__ void load_chunk2(const unsigned char* base, int plane_bytes, int row, int k0, int K, float* v) {
     const int off = il_off(row, k0, K);
-    const uint4 a = *reinterpret_cast<const uint4*>(base + off), b = *reinterpret_cast<const uint4*>(base + plane_bytes + off),
-                c = *reinterpret_cast<const uint4*>(base + 2 * plane_bytes + off);
-    const unsigned pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w}, pc[4] = {c.x, c.y, c.z, c.w};
+    const uint4 a = *reinterpret_cast<const uint4*>(base + off), b = *reinterpret_cast<const uint4*>(base + plane_bytes + off);
+    const unsigned pa[4] = {a.x, a.y, a.z, a.w}, pb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        v[2 * i] = (bf_lo(pa[i]) + bf_lo(pb[i])) + bf_lo(pc[i]);
-        v[2 * i + 1] = (bf_hi(pa[i]) + bf_hi(pb[i])) + bf_hi(pc[i]);
+        float h0, h1, l0, l1;
+        unpack_f16x2(pa[i], h0, h1);
+        unpack_f16x2(pb[i], l0, l1);
+        v[2 * i] = h0 + l0;
+        v[2 * i + 1] = h1 + l1;
     }
 }
 
-// one logical fp32 product block: six bf16 MMAs over the three planes of A and B (same descriptor geometry per plane);
-// hi*hi goes to `d_main`, the five correction products to `d_corr` (see the header).  `ad` / `bd` are the descriptors of
-// the hi planes; the start-address field is the low 14 bits (16-byte units), so another plane or k-block is an integer add.
-__device__ __forceinline__ void mma6(unsigned d_main, unsigned d_corr, unsigned long long ad, unsigned a_plane16,
-                                     unsigned long long bd, unsigned b_plane16, unsigned idesc, int accumulate) {
-    umma_bf16(d_main, ad, bd, idesc, accumulate);                               // hh
-    umma_bf16(d_corr, ad + 2 * a_plane16, bd, idesc, accumulate);               // lh
-    umma_bf16(d_corr, ad, bd + 2 * b_plane16, idesc, 1);                        // hl
-    umma_bf16(d_corr, ad + a_plane16, bd + b_plane16, idesc, 1);                // mm
-    umma_bf16(d_corr, ad + a_plane16, bd, idesc, 1);                            // mh
-    umma_bf16(d_corr, ad, bd + b_plane16, idesc, 1);                            // hm
+// one logical fp32 product block: three fp16 MMAs over the two planes of A and B (same descriptor geometry per plane) into
+// one accumulator.  `ad` / `bd` are the descriptors of the hi planes; the start-address field is the low 14 bits (16-byte
+// units), so the lo plane or another k-block is an integer add.
+__device__ __forceinline__ void mma3(unsigned dt, unsigned long long ad, unsigned a_plane16, unsigned long long bd, unsigned b_plane16,
+                                     unsigned idesc, int accumulate) {
+    umma_bf16(dt, ad, bd, idesc, accumulate);                      // hi.hi   (kind::f16; the operand formats are in idesc)
+    umma_bf16(dt, ad, bd + b_plane16, idesc, 1);                   // hi.lo
+    umma_bf16(dt, ad + a_plane16, bd, idesc, 1);                   // lo.hi
+}
+// kind::f16 instruction descriptor, fp16 x fp16 -> f32, A K-major, B K- or MN-major
+__device__ __forceinline__ unsigned umma_idesc_f16_b(int M, int N, int b_mn_major) {
+    return (1u << 4) | ((unsigned)b_mn_major << 16) | ((unsigned)(N >> 3) << 17) | ((unsigned)(M >> 4) << 24);
+}
+// power-of-two scale that puts a matrix whose largest magnitude is `mx` into [2^e, 2^(e+1))
+__device__ __forceinline__ float pow2_scale(float mx, int e) {
+    return (mx > 0.f && mx < 3.0e38f) ? exp2f((float)(e - ilogbf(mx))) : 1.f;
 }
 
-// v[0..CH) = [ta] + [tb]: two accumulators summed in round-to-nearest fp32, one wait for both loads
-template <int CH>
-__device__ __forceinline__ void tmem_ld_sum(unsigned ta, unsigned tb, float* v) {
-    unsigned r[CH], q[CH];
-    if constexpr (CH == 32) { tmem_ld32_issue(ta, r); tmem_ld32_issue(tb, q); }
-    else { tmem_ld16_issue(ta, r); tmem_ld16_issue(tb, q); }
-    tmem_wait_ld();
-#pragma unroll
-    for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]) + __uint_as_float(q[i]);
-}
 template <int CH>
 __device__ __forceinline__ void tmem_ld(unsigned ta, float* v) {
     unsigned r[CH];
@@ -147,6 +137,16 @@ __device__ __forceinline__ void tmem_ld(unsigned ta, float* v) {
     tmem_wait_ld();
 #pragma unroll
     for (int i = 0; i < CH; ++i) v[i] = __uint_as_float(r[i]);
+}
+// two loads, one wait
+template <int CH>
+__device__ __forceinline__ void tmem_ld2(unsigned ta, float* v, unsigned tb, float* w) {
+    unsigned r[CH], q[CH];
+    if constexpr (CH == 32) { tmem_ld32_issue(ta, r); tmem_ld32_issue(tb, q); }
+    else { tmem_ld16_issue(ta, r); tmem_ld16_issue(tb, q); }
+    tmem_wait_ld();
+#pragma unroll
+    for (int i = 0; i < CH; ++i) { v[i] = __uint_as_float(r[i]); w[i] = __uint_as_float(q[i]); }
 }
 template <int CH>
 __device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
@@ -158,11 +158,11 @@ __device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
 
 // bytes of dynamic shared memory for (mp, KS)
 static inline size_t tc_smem_bytes(int mp, int KS) {
-    return 3 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
+    return 2 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
            sizeof(float) * (2 * (size_t)mp + KS + 32 + 3 * 128);
 }
-static inline int tc_tmem_cols(int mp, int KS) {      // main | corr | tanh(o) | terminal-only S.symb corr
-    int need = 3 * std::max(mp, KS) + KS, c = 32;
+static inline int tc_tmem_cols(int mp, int KS) {      // accumulator | tanh(o) (the terminal evaluation's S.symb' reuses it)
+    int need = 2 * std::max(mp, KS), c = 32;
     while (c < need) c *= 2;
     return c;
 }
@@ -178,52 +178,92 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     const int warp_u = __shfl_sync(0xffffffffu, warp, 0);      // the same value, known to the compiler as warp-uniform
     const int m = A.m, mp = A.mp;
     const ProbPack& pr = A.prob;
-    // shared-memory map (bytes); every operand has three planes (hi, mid, lo)
+    // shared-memory map (bytes); every operand has two planes (hi, lo)
     const int pK1 = mp * mp * 2, pK0 = mp * KS * 2, pX = 128 * mp * 2;
     constexpr int pSy = KS * KS * 2, pS = 128 * KS * 2;
     unsigned char* sK1 = smem;
-    unsigned char* sK0 = sK1 + 3 * pK1;
-    unsigned char* sSy = sK0 + 3 * pK0;
-    unsigned char* sX = sSy + 3 * pSy;
-    unsigned char* sS = sX + 3 * pX;
-    float* sb1 = reinterpret_cast<float*>(sS + 3 * pS);
-    float* sw = sb1 + mp;
+    unsigned char* sK0 = sK1 + 2 * pK1;
+    unsigned char* sSy = sK0 + 2 * pK0;
+    unsigned char* sX = sSy + 2 * pSy;
+    unsigned char* sS = sX + 2 * pX;
+    float* sb1 = reinterpret_cast<float*>(sS + 2 * pS);
+    float* sw = sb1 + mp;                                // w * s_w (see below)
     float* scw = sw + mp;                                // KS floats
     float* sred = scw + KS;                              // 4 warps x 8
     float* sphi = sred + 32;                             // (SPLIT - 1) x 128: partial w.u1 of the other threads of a sample
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned tmem_base_s, tmem_park_s;
+    __shared__ unsigned smax[4];                         // bit patterns of max |K1|, |K0b|, |symb|, |w|
 
-    // ---- one-time per CTA: weights -> split bf16 operands in canonical layout (padded units have zero weights: they
-    //      contribute exactly nothing to any contraction)
+    // ---- one-time per CTA: weights -> scaled, split fp16 operands in canonical layout (padded units have zero weights:
+    //      they contribute exactly nothing to any contraction)
+    // pass 1: symb = [A'A | c_w] in fp32 (parked in the X operand's space, free until the first evaluation) and the largest
+    // magnitude of each matrix
+    float* symb = reinterpret_cast<float*>(sX);          // [KS][KS], symb[n = k'][k]: (A'A)[k][k'] | c_w[k'] in column D | 0
+    if (tid < 4) smax[tid] = 0u;
+    __syncthreads();
+    {
+        float m1 = 0.f, m0 = 0.f, ms = 0.f, mw = 0.f;
+        for (int i = tid; i < m * m; i += NT) m1 = fmaxf(m1, fabsf(A.K1[i]));
+        for (int i = tid; i < m * D; i += NT) m0 = fmaxf(m0, fabsf(A.K0[i]));
+        for (int i = tid; i < m; i += NT) { m0 = fmaxf(m0, fabsf(A.b0[i])); mw = fmaxf(mw, fabsf(A.w[i])); }
+        for (int i = tid; i < KS * KS; i += NT) {
+            const int kp = i / KS, k = i % KS;
+            float v = 0.f;
+            if (kp < D && k < D) { for (int q = 0; q < A.r; ++q) v = fmaf(A.A[q * D + k], A.A[q * D + kp], v); }
+            else if (kp < D && k == D) v = A.c_w[kp];
+            symb[i] = v;
+            ms = fmaxf(ms, fabsf(v));
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, off)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, off));
+            ms = fmaxf(ms, __shfl_xor_sync(0xffffffffu, ms, off)); mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+        }
+        if ((tid & 31) == 0) {                           // non-negative floats order like their bit patterns (NaN sorts above inf)
+            atomicMax(&smax[0], __float_as_uint(m1)); atomicMax(&smax[1], __float_as_uint(m0));
+            atomicMax(&smax[2], __float_as_uint(ms)); atomicMax(&smax[3], __float_as_uint(mw));
+        }
+    }
+    __syncthreads();
+    // Scales (powers of two, the same in every thread and every CTA).  K1 -> s1.  Y and V carry s_w (w is stored pre-scaled, so
+    // the epilogues pay nothing for it), hence GEMM-4's accumulator holds s_w s0 g and symb, which lands in the same
+    // accumulator from the unscaled S, is scaled by s_w s0; s0 keeps both K0b and that product below 2^14.
+    const float s_w = pow2_scale(__uint_as_float(smax[3]), 6);
+    const float s1 = pow2_scale(__uint_as_float(smax[0]), 13);
+    const float sx = A.sx;
+    const float s0 = pow2_scale(fmaxf(__uint_as_float(smax[1]), __uint_as_float(smax[2]) * (s_w / sx)), 13);
+    const float ssy = s0 * s_w;                          // scale of GEMM-4's accumulator; symb itself carries ssy / sx
+    // reciprocal scales with the accumulate-bias compensation of each contraction folded in (3 MMAs per 16-deep k-block)
+    const float kShrink = 1.89e-8f * A.bias_f;
+    const float r_o = (1.f / (s0 * sx)) * (1.f + kShrink * 3.f * (KS / 16));             // GEMM-1: o = acc r_o
+    const float r_a = (1.f / s1) * (1.f + kShrink * 3.f * (mp / 16));                    // GEMM-2: a1 = acc r_a;  GEMM-3: s_w z1 = acc r_a
+    const float r_g = (1.f / ssy) * (1.f + kShrink * 3.f * ((mp + KS) / 16));            // GEMM-4: g = acc r_g
+    const float r_q = (1.f / ssy) * (1.f + kShrink * 3.f * (KS / 16));                   // terminal S.symb' on its own
+    const float hz = A.h * r_a;                          // s_w v = tanh(o) (s_w w + h (s_w z1))
+    const float inv_sw = 1.f / s_w, ssym = ssy / sx;
     for (int i = tid; i < mp * (mp / 8); i += NT) {     // K1[o][k0..k0+8)
         const int o = i / (mp / 8), k0 = (i % (mp / 8)) * 8;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = (o < m && k0 + e < m) ? A.K1[o * m + k0 + e] : 0.f;
-        store_chunk3(sK1, pK1, o, k0, mp, v);
+        for (int e = 0; e < 8; ++e) v[e] = (o < m && k0 + e < m) ? A.K1[o * m + k0 + e] * s1 : 0.f;
+        store_chunk2(sK1, pK1, o, k0, mp, v);
     }
     for (int i = tid; i < mp * (KS / 8); i += NT) {     // K0b[j][k]: K0 | b0 | 0
         const int j = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { const int k = k0 + e; v[e] = (j >= m) ? 0.f : ((k < D) ? A.K0[j * D + k] : (k == D ? A.b0[j] : 0.f)); }
-        store_chunk3(sK0, pK0, j, k0, KS, v);
+        for (int e = 0; e < 8; ++e) { const int k = k0 + e; v[e] = (j >= m) ? 0.f : ((k < D) ? A.K0[j * D + k] : (k == D ? A.b0[j] : 0.f)) * s0; }
+        store_chunk2(sK0, pK0, j, k0, KS, v);
     }
-    for (int i = tid; i < KS * (KS / 8); i += NT) {     // symb[n = k'][k]: (A'A)[k][k'] | c_w[k'] in column D | 0
+    for (int i = tid; i < KS * (KS / 8); i += NT) {
         const int kp = i / (KS / 8), k0 = (i % (KS / 8)) * 8;
         float v[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const int k = k0 + e;
-            float s = 0.f;
-            if (kp < D && k < D) { for (int q = 0; q < A.r; ++q) s = fmaf(A.A[q * D + k], A.A[q * D + kp], s); }
-            else if (kp < D && k == D) s = A.c_w[kp];
-            v[e] = s;
-        }
-        store_chunk3(sSy, pSy, kp, k0, KS, v);
+        for (int e = 0; e < 8; ++e) v[e] = symb[kp * KS + k0 + e] * ssym;
+        store_chunk2(sSy, pSy, kp, k0, KS, v);
     }
-    for (int i = tid; i < mp; i += NT) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] : 0.f; }
+    for (int i = tid; i < mp; i += NT) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] * s_w : 0.f; }
     if (tid < KS) scw[tid] = (tid < D) ? A.c_w[tid] : 0.f;
     if (warp == 0) {
         const bool own = SH::PARK && A.park_col < 0;
@@ -236,19 +276,17 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     __syncthreads();
     tc_fence_after();
     const int C = (mp > KS) ? mp : KS;
-    const unsigned tacc = tmem_base_s;                   // hi*hi accumulator, columns [0, C)
+    const unsigned tacc = tmem_base_s;                   // the accumulator, columns [0, C)
     const unsigned tpark = !SH::PARK ? 0u : (A.park_col < 0 ? tmem_park_s : tacc + (unsigned)A.park_col) + (unsigned)(hf * SH::PW);
-    const unsigned tcor = tacc + C;                      // correction-term accumulator, same column map
-    const unsigned tT0 = tacc + 2 * C;                   // tanh(o); at the terminal evaluation also S.symb' (main)
-    const unsigned tTq = tacc + 3 * C;                   // terminal evaluation only: S.symb' (corrections), KS columns
+    const unsigned tT0 = tacc + C;                       // tanh(o); at the terminal evaluation afterwards S.symb'
     const unsigned lane_bits = (unsigned)((warp & 3) * 32) << 16;
     const unsigned mb = smem_u32(&mbar);
     int phase = 0;
-    const unsigned idesc_m_k = umma_idesc_bf16(128, mp, 0), idesc_m_mn = umma_idesc_bf16(128, mp, 1);
-    const unsigned idesc_s_mn = umma_idesc_bf16(128, KS, 1), idesc_s_k = umma_idesc_bf16(128, KS, 0);
+    const unsigned idesc_m_k = umma_idesc_f16_b(128, mp, 0), idesc_m_mn = umma_idesc_f16_b(128, mp, 1);
+    const unsigned idesc_s_mn = umma_idesc_f16_b(128, KS, 1), idesc_s_k = umma_idesc_f16_b(128, KS, 0);
     const unsigned sboM = (unsigned)(mp >> 3) * 128;     // 8-row-group stride of an operand with K = mp
     constexpr unsigned sboS = (unsigned)(KS >> 3) * 128; // ... with K = KS
-    // hi-plane descriptors (k-block 0); planes and k-blocks are reached by adding 16-byte-unit offsets
+    // hi-plane descriptors (k-block 0); the lo plane and k-blocks are reached by adding 16-byte-unit offsets
     const unsigned long long dX = umma_desc(smem_u32(sX), 128, sboM), dS = umma_desc(smem_u32(sS), 128, sboS);
     const unsigned long long dK1k = umma_desc(smem_u32(sK1), 128, sboM), dK1n = umma_desc(smem_u32(sK1), sboM, 128);
     const unsigned long long dK0k = umma_desc(smem_u32(sK0), 128, sboS), dK0n = umma_desc(smem_u32(sK0), sboS, 128);
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     constexpr unsigned kK0n = (2 * sboS) >> 4;           // ... of K0b read MN-major
 
     // publish my operand writes and let thread 0 issue `issue`; mma_wait() then blocks until the tensor core is done
-    // The issuing warp rotates with the GEMM (warp g issues GEMM-g): the ~25 instructions per mma6 are then spread over
+    // The issuing warp rotates with the GEMM (warp g issues GEMM-g): the MMA issue instructions are then spread over
     // four warps instead of lengthening warp 0's critical path in every round.  Ordering is safe: each GEMM is issued
     // after a block barrier that follows every thread's wait on the previous GEMM's commit.
     auto mma_issue = [&](int who, auto issue) {
@@ -351,35 +389,35 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             if (SPLIT > 1 && ((c0 >> 3) % SPLIT) != hf) continue;
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = (k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f)); }
-            store_chunk3(sS, pS, row, c0, KS, v);
+            for (int e = 0; e < 8; ++e) { const int k = c0 + e; v[e] = sx * ((k < d) ? xs[k < d ? k : 0] : (k == d ? t : (k == D ? 1.f : 0.f))); }
+            store_chunk2(sS, pS, row, c0, KS, v);
         }
-        mma_issue(0, [&] {                               // GEMM-1: O = S . K0b'
+        mma_issue(0, [&] {                               // GEMM-1: s0 O = S . K0b'
 #pragma unroll
-            for (int kb = 0; kb < KS / 16; ++kb) mma6(tacc, tcor, dS + kb * 16, qS, dK0k + kb * 16, qK0, idesc_m_k, kb > 0);
+            for (int kb = 0; kb < KS / 16; ++kb) mma3(tacc, dS + kb * 16, qS, dK0k + kb * 16, qK0, idesc_m_k, kb > 0);
         });
         if (!terminal) problem_x(xs, xq);
         mma_wait();
         for (int c0 = cbeg; c0 < cend; c0 += CH) {            // u0 = act(o) -> X operand, tanh(o) -> TMEM
             float v[CH], tt[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+            tmem_ld<CH>(tacc + lane_bits + c0, v);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) act_tanh(v[i], v[i], tt[i]);
+            for (int i = 0; i < CH; ++i) act_tanh(v[i] * r_o, v[i], tt[i]);
             tmem_st<CH>(tT0 + lane_bits + c0, tt);
 #pragma unroll
-            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+            for (int q = 0; q < CH / 8; ++q) store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
         }
-        run_mma(1, [&] {                                 // GEMM-2: A1 = U0 . K1'  (B K-major)
-            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1k + kb * 16, qK1, idesc_m_k, kb > 0);
+        run_mma(1, [&] {                                 // GEMM-2: s1 A1 = U0 . K1'  (B K-major)
+            for (int kb = 0; kb < mp / 16; ++kb) mma3(tacc, dX + kb * 16, qX, dK1k + kb * 16, qK1, idesc_m_k, kb > 0);
         });
         float phiN = 0.f;
-        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // y = tanh(a1 + b1) * w -> X operand
+        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // s_w y = tanh(a1 + b1) * (s_w w) -> X operand
             float v[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
+            tmem_ld<CH>(tacc + lane_bits + c0, v);
 #pragma unroll
             for (int q = 0; q < CH / 8; ++q) {
                 float u8[8];
-                if (terminal) load_chunk3(sX, pX, row, c0 + q * 8, mp, u8);      // u0, before it is overwritten
+                if (terminal) load_chunk2(sX, pX, row, c0 + q * 8, mp, u8);      // u0, before it is overwritten
                 float b8[8], w8[8];                       // 16-byte loads of the bias and w (16-byte aligned by construction)
                 *reinterpret_cast<float4*>(b8) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8);
                 *reinterpret_cast<float4*>(b8 + 4) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8 + 4);
@@ -387,62 +425,66 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
                 *reinterpret_cast<float4*>(w8 + 4) = *reinterpret_cast<const float4*>(sw + c0 + q * 8 + 4);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float pre = v[q * 8 + e] + b8[e], wv = w8[e];
+                    const float pre = fmaf(v[q * 8 + e], r_a, b8[e]), wv = w8[e];
                     if (terminal) {
                         float av, tv;
                         act_tanh(pre, av, tv);
-                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);
+                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);        // s_w w.u1 (unscaled at the end)
                         v[q * 8 + e] = tv * wv;
                     } else {
                         v[q * 8 + e] = tanh_only(pre) * wv;
                     }
                 }
-                store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+                store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
             }
         }
         if (SPLIT > 1 && terminal && hf > 0) sphi[(hf - 1) * 128 + row] = phiN;
-        run_mma(2, [&] {                                 // GEMM-3: Z1 = Y . K1  (the same buffer, MN-major)
-            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK1n + kb * kK1n, qK1, idesc_m_mn, kb > 0);
+        run_mma(2, [&] {                                 // GEMM-3: s_w s1 Z1 = (s_w Y) . K1  (the same buffer, MN-major)
+            for (int kb = 0; kb < mp / 16; ++kb) mma3(tacc, dX + kb * 16, qX, dK1n + kb * kK1n, qK1, idesc_m_mn, kb > 0);
         });
-        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // v = tanh(o) * (w + h z1acc) -> X operand
+        for (int c0 = cbeg; c0 < cend; c0 += CH) {            // s_w v = tanh(o) * (s_w w + h s_w z1acc) -> X operand
             float v[CH], tt[CH];
-            tmem_ld_sum<CH>(tacc + lane_bits + c0, tcor + lane_bits + c0, v);
-            tmem_ld<CH>(tT0 + lane_bits + c0, tt);
+            tmem_ld2<CH>(tacc + lane_bits + c0, v, tT0 + lane_bits + c0, tt);
 #pragma unroll
             for (int i = 0; i < CH; i += 4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(sw + c0 + i);
-                v[i] = tt[i] * (w4.x + A.h * v[i]); v[i + 1] = tt[i + 1] * (w4.y + A.h * v[i + 1]);
-                v[i + 2] = tt[i + 2] * (w4.z + A.h * v[i + 2]); v[i + 3] = tt[i + 3] * (w4.w + A.h * v[i + 3]);
+                v[i] = tt[i] * fmaf(hz, v[i], w4.x); v[i + 1] = tt[i + 1] * fmaf(hz, v[i + 1], w4.y);
+                v[i + 2] = tt[i + 2] * fmaf(hz, v[i + 2], w4.z); v[i + 3] = tt[i + 3] * fmaf(hz, v[i + 3], w4.w);
             }
 #pragma unroll
-            for (int q = 0; q < CH / 8; ++q) store_chunk3(sX, pX, row, c0 + q * 8, mp, v + q * 8);
+            for (int q = 0; q < CH / 8; ++q) store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
         }
-        run_mma(3, [&] {                                 // GEMM-4: G = V . K0b (MN-major view) + S . symb'
-            for (int kb = 0; kb < mp / 16; ++kb) mma6(tacc, tcor, dX + kb * 16, qX, dK0n + kb * kK0n, qK0, idesc_s_mn, kb > 0);
+        run_mma(3, [&] {                                 // GEMM-4: s_w s0 G = (s_w V) . K0b (MN-major view) + S . (s_w s0 symb)'
+            for (int kb = 0; kb < mp / 16; ++kb) mma3(tacc, dX + kb * 16, qX, dK0n + kb * kK0n, qK0, idesc_s_mn, kb > 0);
             // the terminal evaluation needs S.symb' on its own (Phi's quadratic term): it goes to the free tanh columns
-            const unsigned qm = terminal ? tT0 : tacc, qc = terminal ? tTq : tcor;
+            const unsigned qm = terminal ? tT0 : tacc;
 #pragma unroll
-            for (int kb = 0; kb < KS / 16; ++kb) mma6(qm, qc, dS + kb * 16, qS, dSy + kb * 16, qSy, idesc_s_k, terminal ? (kb > 0) : 1);
+            for (int kb = 0; kb < KS / 16; ++kb) mma3(qm, dS + kb * 16, qS, dSy + kb * 16, qSy, idesc_s_k, terminal ? (kb > 0) : 1);
         });
+        const float rg = terminal ? (1.f / ssy) * (1.f + kShrink * 3.f * (mp / 16)) : r_g;
 #pragma unroll
-        for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tacc + lane_bits + c0, tcor + lane_bits + c0, g + c0);
+        for (int c0 = 0; c0 < KS; c0 += 16) {
+            tmem_ld<16>(tacc + lane_bits + c0, g + c0);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g[c0 + i] *= rg;
+        }
         if (terminal) {                                   // Phi = w.u1 + 0.5 s'A'A s + c_w.s + c_b  (Phi.py:96)
             float gq[KS];
 #pragma unroll
-            for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld_sum<16>(tT0 + lane_bits + c0, tTq + lane_bits + c0, gq + c0);
+            for (int c0 = 0; c0 < KS; c0 += 16) tmem_ld<16>(tT0 + lane_bits + c0, gq + c0);
             float quad = 0.f, lin = 0.f;
 #pragma unroll
             for (int k = 0; k < D; ++k) {
-                const float sv = (k < d) ? xs[k < d ? k : 0] : t;
-                quad = fmaf(sv, gq[k] - scw[k], quad);   // gq carries c_w (column D of symb)
+                const float sv = (k < d) ? xs[k < d ? k : 0] : t, gk = gq[k] * r_q;
+                quad = fmaf(sv, gk - scw[k], quad);      // gq carries c_w (column D of symb)
                 lin = fmaf(scw[k], sv, lin);
-                g[k] += gq[k];
+                g[k] += gk;
             }
             if (SPLIT > 1) {                              // written before GEMM-3's barrier; only the hf = 0 thread's sum is used
 #pragma unroll
                 for (int q = 1; q < SPLIT; ++q) phiN += sphi[(q - 1) * 128 + row];
             }
-            phi_out = phiN + 0.5f * quad + (lin + A.c_b[0]);
+            phi_out = phiN * inv_sw + 0.5f * quad + (lin + A.c_b[0]);
         }
     };
 
@@ -683,11 +725,18 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     NOC_CUDA(cudaGetDevice(&dev));
     NOC_CUDA(cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev));
     NOC_CUDA(cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev));
-    // TMEM columns: main | corr | tanh(o) | terminal-only S.symb corr, in one power-of-two block; PARK shapes add the parked
+    // TMEM columns: accumulator | tanh(o), in one power-of-two block; PARK shapes add the parked
     // RK accumulator: in the block's spare columns when there are any, else (one thread per sample, 32 columns) in a second
     // 32-column block so that e.g. swap12 stays at 160 columns = 3 CTAs per SM, else by growing the block
-    const int tmem_used = 3 * std::max(A.mp, SH::KS) + SH::KS, park_need = SH::PW * SH::SPLIT;
+    const int tmem_used = 2 * std::max(A.mp, SH::KS), park_need = SH::PW * SH::SPLIT;
     A.tmem_cols = tc_tmem_cols(A.mp, SH::KS);
+    {   // scale 2^e of the S operand (states beyond 2^(15-e) would overflow fp16: 1024 at the default; experiments: NOC_TC_SX = e)
+        int ex = 5;
+        if (const char* e = getenv("NOC_TC_SX")) ex = atoi(e);
+        A.sx = ldexpf(1.f, ex);
+        A.bias_f = 1.f;
+        if (const char* e = getenv("NOC_TC_BIAS")) A.bias_f = (float)atof(e);
+    }
     A.park_col = -1;
     if (SH::PARK) {
         if (A.tmem_cols - tmem_used >= park_need) A.park_col = tmem_used;

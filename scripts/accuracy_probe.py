@@ -14,14 +14,19 @@ from oracle import ocflow_oracle as orc
 torch.set_num_threads(os.cpu_count())
 print("library:", nb._cabi.LIB_PATH)
 ONLY = os.environ.get("PROBE_ONLY")
+NT = int(os.environ.get("PROBE_NT", "0"))
+SEED = int(os.environ.get("PROBE_SEED", "77"))
+NS = int(os.environ.get("PROBE_N", "0"))
 for name, n, nt in (("softcorridor", 512, 50), ("swap2", 512, 50), ("swap12", 512, 50), ("singlequad", 512, 50), ("swarm50", 256, 80)):
     if ONLY and name != ONLY:
         continue
+    nt = NT or nt
+    n = NS or n
     net, prob, xinit, meta = product_setup(name, torch.float32)
     P32, D32, _, _ = oracle_setup(name, torch.float32)
     P64, D64, _, _ = oracle_setup(name, torch.float64)
     d = xinit.shape[1]
-    g = torch.Generator().manual_seed(77)
+    g = torch.Generator().manual_seed(SEED)
     if name == "singlequad":
         x = torch.zeros(n, d); x[:, :3] = -1.5 + meta["var0"] * torch.randn(n, 3, generator=g)
     else:

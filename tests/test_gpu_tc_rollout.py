@@ -86,7 +86,7 @@ def _vs_tile(nb, monkeypatch, net, prob, x, alph, nt, d, full):
     assert bad <= (2 if len(tt) >= 1000 else 0), "per-sample costs tc vs fma: %d rows differ" % bad
     check_costs(mt, tt.mean(axis=0), 1e-6, 1e-7, "tc mean vs mean of tc noMean", floor_mask=QW)
     if full:
-        assert rel_state_err(zt.cpu().numpy(), zf.cpu().numpy(), d) <= 5e-6
+        assert rel_state_err(zt.cpu().numpy(), zf.cpu().numpy(), d) <= 1e-5      # two fp32 kernels, each 3-5e-6 from fp64 on singlequad
         assert (ut - uf).abs().max() <= 1e-4 * max(1.0, float(uf.abs().max()))
 
 

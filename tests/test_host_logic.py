@@ -136,9 +136,9 @@ def test_bench_flop_accounting():
             "swarm50": (150, 512, 5455456)}
     for name, (d, m, f) in want.items():
         assert b.flops_per_sample_step(d, m, 2, min(10, d + 1)) == f, name
-    assert b.tensor_flops_per_sample_step("swap12", 24, 32)[0] == 4 * 6 * 2 * (32 * 32 + 2 * 32 * 32 + 32 * 32 + 32 * 32)
-    assert b.tensor_flops_per_sample_step("singlequad", 12, 128)[0] == 4 * 6 * 2 * (16 * 128 + 2 * 128 * 128 + 128 * 16 + 16 * 16)
-    assert b.tensor_flops_per_sample_step("swap2", 4, 16)[0] == 4 * 6 * 2 * (16 * 16 * 5)
+    assert b.tensor_flops_per_sample_step("swap12", 24, 32)[0] == 4 * 3 * 2 * (32 * 32 + 2 * 32 * 32 + 32 * 32 + 32 * 32)
+    assert b.tensor_flops_per_sample_step("singlequad", 12, 128)[0] == 4 * 3 * 2 * (16 * 128 + 2 * 128 * 128 + 128 * 16 + 16 * 16)
+    assert b.tensor_flops_per_sample_step("swap2", 4, 16)[0] == 4 * 3 * 2 * (16 * 16 * 5)
     assert b.tensor_flops_per_sample_step("singlequad", 12, 100)[0] == b.tensor_flops_per_sample_step("singlequad", 12, 128)[0]   # width padded to 64s
     # streamed swarm kernel: 3 split products (fp16 x 2), KS = 160, m = 512
     assert b.tensor_flops_per_sample_step("swarm50", 150, 512)[0] == 4 * 3 * 2 * (2 * 160 * 512 + 2 * 512 * 512 + 160 * 160)
