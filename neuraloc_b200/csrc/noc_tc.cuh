@@ -240,4 +240,39 @@ __device__ __forceinline__ void split2_f16(float a, float b, unsigned& hi, unsig
     hi = h;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Packed-fp32 epilogue math (FFMA2 / FADD2 / FMUL2, sm_100+): the activation epilogues of the tensor kernels are bound by
+// instruction issue, and two neighbouring hidden units of one sample sit in neighbouring registers after tcgen05.ld.
+// Same approximate MUFU transcendentals as act_tanh<float> / tanh_only<float> (noc_types.cuh); per element 7.5, 4 and 1
+// instructions for the three epilogues instead of 10, 9 and 2.
+// ------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float tc_ex2(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tc_lg2(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float tc_rcp(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+constexpr float kTwoLog2e = 2.885390081777927f;          // 2 log2(e): exp(2x) = 2^(kTwoLog2e x)
+// act = |pre| + ln(1 + exp(-2|pre|)) (the antiderivative of tanh, Phi.py:8-12), th = tanh(pre), for pre = acc * r
+__device__ __forceinline__ void act_tanh2(float2 acc, float2 r, float2& act, float2& th) {
+    const float2 pre = __fmul2_rn(acc, r);
+    float2 e;
+    e.x = tc_ex2(fabsf(pre.x) * -kTwoLog2e);
+    e.y = tc_ex2(fabsf(pre.y) * -kTwoLog2e);
+    const float2 den = __fadd2_rn(e, make_float2(1.f, 1.f));
+    act.x = fmaf(tc_lg2(den.x), 0.6931471805599453f, fabsf(pre.x));
+    act.y = fmaf(tc_lg2(den.y), 0.6931471805599453f, fabsf(pre.y));
+    float2 q;
+    q.x = tc_rcp(den.x); q.y = tc_rcp(den.y);
+    const float2 t = __ffma2_rn(q, make_float2(2.f, 2.f), make_float2(-1.f, -1.f));     // (1 - e) / (1 + e) = 2 / (1 + e) - 1
+    th.x = copysignf(t.x, pre.x); th.y = copysignf(t.y, pre.y);
+}
+// tanh(acc * r + b) * w with r and b pre-multiplied by 2 log2(e):  tanh(x) = 1 - 2 / (1 + exp(2x)), no sign handling
+// (exp(2x) = inf gives 1, 0 gives -1)
+__device__ __forceinline__ float2 tanh2_w(float2 acc, float2 rc, float2 bc, float2 w) {
+    const float2 p = __ffma2_rn(acc, rc, bc);
+    float2 e, q;
+    e.x = tc_ex2(p.x); e.y = tc_ex2(p.y);
+    const float2 den = __fadd2_rn(e, make_float2(1.f, 1.f));
+    q.x = tc_rcp(den.x); q.y = tc_rcp(den.y);
+    return __fmul2_rn(__ffma2_rn(q, make_float2(-2.f, -2.f), make_float2(1.f, 1.f)), w);
+}
+
 }  // namespace noc

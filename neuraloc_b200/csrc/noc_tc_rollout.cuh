@@ -159,7 +159,7 @@ __device__ __forceinline__ void tmem_st(unsigned ta, const float* v) {
 // bytes of dynamic shared memory for (mp, KS)
 static inline size_t tc_smem_bytes(int mp, int KS) {
     return 2 * ((size_t)mp * mp * 2 + (size_t)mp * KS * 2 + (size_t)KS * KS * 2 + (size_t)128 * mp * 2 + (size_t)128 * KS * 2) +
-           sizeof(float) * (2 * (size_t)mp + KS + 32 + 3 * 128);
+           sizeof(float) * (3 * (size_t)mp + KS + 32 + 3 * 128);
 }
 static inline int tc_tmem_cols(int mp, int KS) {      // accumulator | tanh(o) (the terminal evaluation's S.symb' reuses it)
     int need = 2 * std::max(mp, KS), c = 32;
@@ -187,7 +187,8 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     unsigned char* sX = sSy + 2 * pSy;
     unsigned char* sS = sX + 2 * pX;
     float* sb1 = reinterpret_cast<float*>(sS + 2 * pS);
-    float* sw = sb1 + mp;                                // w * s_w (see below)
+    float* sb1c = sb1 + mp;                              // b1 * 2 log2(e): the bias as tanh2_w() wants it
+    float* sw = sb1c + mp;                               // w * s_w (see below)
     float* scw = sw + mp;                                // KS floats
     float* sred = scw + KS;                              // 4 warps x 8
     float* sphi = sred + 32;                             // (SPLIT - 1) x 128: partial w.u1 of the other threads of a sample
@@ -240,6 +241,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     const float r_a = (1.f / s1) * (1.f + kShrink * 3.f * (mp / 16));                    // GEMM-2: a1 = acc r_a;  GEMM-3: s_w z1 = acc r_a
     const float r_g = (1.f / ssy) * (1.f + kShrink * 3.f * ((mp + KS) / 16));            // GEMM-4: g = acc r_g
     const float r_q = (1.f / ssy) * (1.f + kShrink * 3.f * (KS / 16));                   // terminal S.symb' on its own
+    const float r_ac = r_a * kTwoLog2e;                  // ... for tanh2_w()
     const float hz = A.h * r_a;                          // s_w v = tanh(o) (s_w w + h (s_w z1))
     const float inv_sw = 1.f / s_w, ssym = ssy / sx;
     for (int i = tid; i < mp * (mp / 8); i += NT) {     // K1[o][k0..k0+8)
@@ -263,7 +265,10 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         for (int e = 0; e < 8; ++e) v[e] = symb[kp * KS + k0 + e] * ssym;
         store_chunk2(sSy, pSy, kp, k0, KS, v);
     }
-    for (int i = tid; i < mp; i += NT) { sb1[i] = (i < m) ? A.b1[i] : 0.f; sw[i] = (i < m) ? A.w[i] * s_w : 0.f; }
+    for (int i = tid; i < mp; i += NT) {
+        const float bv = (i < m) ? A.b1[i] : 0.f;
+        sb1[i] = bv; sb1c[i] = bv * kTwoLog2e; sw[i] = (i < m) ? A.w[i] * s_w : 0.f;
+    }
     if (tid < KS) scw[tid] = (tid < D) ? A.c_w[tid] : 0.f;
     if (warp == 0) {
         const bool own = SH::PARK && A.park_col < 0;
@@ -402,7 +407,11 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             float v[CH], tt[CH];
             tmem_ld<CH>(tacc + lane_bits + c0, v);
 #pragma unroll
-            for (int i = 0; i < CH; ++i) act_tanh(v[i] * r_o, v[i], tt[i]);
+            for (int i = 0; i < CH; i += 2) {
+                float2 av, tv;
+                act_tanh2(make_float2(v[i], v[i + 1]), make_float2(r_o, r_o), av, tv);
+                v[i] = av.x; v[i + 1] = av.y; tt[i] = tv.x; tt[i + 1] = tv.y;
+            }
             tmem_st<CH>(tT0 + lane_bits + c0, tt);
 #pragma unroll
             for (int q = 0; q < CH / 8; ++q) store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
@@ -419,20 +428,25 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
                 float u8[8];
                 if (terminal) load_chunk2(sX, pX, row, c0 + q * 8, mp, u8);      // u0, before it is overwritten
                 float b8[8], w8[8];                       // 16-byte loads of the bias and w (16-byte aligned by construction)
-                *reinterpret_cast<float4*>(b8) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8);
-                *reinterpret_cast<float4*>(b8 + 4) = *reinterpret_cast<const float4*>(sb1 + c0 + q * 8 + 4);
+                const float* sb = terminal ? sb1 : sb1c;
+                *reinterpret_cast<float4*>(b8) = *reinterpret_cast<const float4*>(sb + c0 + q * 8);
+                *reinterpret_cast<float4*>(b8 + 4) = *reinterpret_cast<const float4*>(sb + c0 + q * 8 + 4);
                 *reinterpret_cast<float4*>(w8) = *reinterpret_cast<const float4*>(sw + c0 + q * 8);
                 *reinterpret_cast<float4*>(w8 + 4) = *reinterpret_cast<const float4*>(sw + c0 + q * 8 + 4);
+                if (terminal) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float pre = fmaf(v[q * 8 + e], r_a, b8[e]), wv = w8[e];
-                    if (terminal) {
+                    for (int e = 0; e < 8; ++e) {
                         float av, tv;
-                        act_tanh(pre, av, tv);
-                        phiN = fmaf(wv, u8[e] + A.h * av, phiN);        // s_w w.u1 (unscaled at the end)
-                        v[q * 8 + e] = tv * wv;
-                    } else {
-                        v[q * 8 + e] = tanh_only(pre) * wv;
+                        act_tanh(fmaf(v[q * 8 + e], r_a, b8[e]), av, tv);
+                        phiN = fmaf(w8[e], u8[e] + A.h * av, phiN);        // s_w w.u1 (unscaled at the end)
+                        v[q * 8 + e] = tv * w8[e];
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const float2 y = tanh2_w(make_float2(v[q * 8 + e], v[q * 8 + e + 1]), make_float2(r_ac, r_ac),
+                                                 make_float2(b8[e], b8[e + 1]), make_float2(w8[e], w8[e + 1]));
+                        v[q * 8 + e] = y.x; v[q * 8 + e + 1] = y.y;
                     }
                 }
                 store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
@@ -448,8 +462,9 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
 #pragma unroll
             for (int i = 0; i < CH; i += 4) {
                 const float4 w4 = *reinterpret_cast<const float4*>(sw + c0 + i);
-                v[i] = tt[i] * fmaf(hz, v[i], w4.x); v[i + 1] = tt[i + 1] * fmaf(hz, v[i + 1], w4.y);
-                v[i + 2] = tt[i + 2] * fmaf(hz, v[i + 2], w4.z); v[i + 3] = tt[i + 3] * fmaf(hz, v[i + 3], w4.w);
+                const float2 a = __fmul2_rn(make_float2(tt[i], tt[i + 1]), __ffma2_rn(make_float2(hz, hz), make_float2(v[i], v[i + 1]), make_float2(w4.x, w4.y)));
+                const float2 b = __fmul2_rn(make_float2(tt[i + 2], tt[i + 3]), __ffma2_rn(make_float2(hz, hz), make_float2(v[i + 2], v[i + 3]), make_float2(w4.z, w4.w)));
+                v[i] = a.x; v[i + 1] = a.y; v[i + 2] = b.x; v[i + 3] = b.y;
             }
 #pragma unroll
             for (int q = 0; q < CH / 8; ++q) store_chunk2(sX, pX, row, c0 + q * 8, mp, v + q * 8);
@@ -466,7 +481,10 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
         for (int c0 = 0; c0 < KS; c0 += 16) {
             tmem_ld<16>(tacc + lane_bits + c0, g + c0);
 #pragma unroll
-            for (int i = 0; i < 16; ++i) g[c0 + i] *= rg;
+            for (int i = 0; i < 16; i += 2) {
+                const float2 gg = __fmul2_rn(make_float2(g[c0 + i], g[c0 + i + 1]), make_float2(rg, rg));
+                g[c0 + i] = gg.x; g[c0 + i + 1] = gg.y;
+            }
         }
         if (terminal) {                                   // Phi = w.u1 + 0.5 s'A'A s + c_w.s + c_b  (Phi.py:96)
             float gq[KS];
