@@ -171,6 +171,27 @@ int noc_sample_rho0(const void* center, int32_t d, int32_t noise_cols, double va
  * counter blocks group0 .. group0 + ngroups - 1 (counter = (lo32, hi32, 0, 0), key = (lo32(seed), hi32(seed))). */
 int noc_philox_raw(uint64_t seed, int64_t group0, int64_t ngroups, void* out_u32, void* stream);
 
+/*
+ * noc_ocflow_grad — replaces one training evaluation, `Jc, cs = OCflow(x0, net, prob, tspan, nt, "rk4", alph); Jc.backward()`
+ * (trainOC.py:172-173): the rollout of noc_ocflow in mean mode AND the exact reverse-mode gradient of the sum over the samples
+ * of the per-sample objective  L + alph[0] G + alph[3] HJt + alph[4] HJfin + alph[5] HJgrad  (OCflow.py:75) with respect to every
+ * Phi parameter and, optionally, the initial states — the discrete adjoint of stepRK4 (OCflow.py:157-184) with the second-order
+ * terms of Phi.getGrad (Phi.py:99-138) and the derivatives of calcLHQW / calcGradpH (train- or eval-mode, as prob->training
+ * says).  One kernel launch (forward sweep, terminal block, backward sweep) + a weight-packing kernel + the cost reduction.
+ * nTh == 2 and stepper 'rk4' only; Quadcopter with one agent only (NOC_ERR_UNSUPPORTED otherwise).
+ *
+ *   out_costs  dev [8] DOUBLE: sums of [L, G, HJt, HJfin, HJgrad, Q, W] and the sample count, as noc_ocflow's mean mode
+ *   grad       dev [P] dtype-typed, P = r D + D + 1 + m + m D + m + m m + m: SUMS over the samples of d objective / d parameter,
+ *              concatenated in the reference's state_dict order (Phi.py:77-87): A, c.weight, c.bias, w.weight,
+ *              N.layers.0.weight, N.layers.0.bias, N.layers.1.weight, N.layers.1.bias.  Divide by the sample count for the
+ *              gradient of the reference's mean objective (sums so that shards add).  Overwritten, not accumulated.
+ *              Accumulated with floating-point atomics: reproducible to rounding, not bitwise.
+ *   grad_x     dev [n, d] or NULL: d (sample's objective) / d x
+ */
+int noc_ocflow_grad(const noc_phi_t* phi, const noc_prob_t* prob, const void* x, int64_t n,
+                    const double* stage_times, double t0, double t1, int32_t nt, const double* alph, int32_t dtype,
+                    void* out_costs, void* grad, void* grad_x, void* stream);
+
 /* Which kernel family the calling thread's last noc_ocflow / noc_ocflow_host call ran (-1 before the first call):
  * the FMA sample-tile kernel, the one-CTA-per-sample small-batch kernel, or the tensor-core kernel.  The choice is made
  * from the shapes and the batch size; env NOC_TC=0 disables the tensor-core kernel, NOC_FORCE_PATH=tile|vec|tc pins one. */

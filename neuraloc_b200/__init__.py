@@ -9,7 +9,7 @@ Everything numeric runs in hand-written CUDA (libnoc_b200.so, C ABI in include/n
 sm_100a device.  There is no CPU implementation: importing works anywhere, calling needs the built
 library and a GPU and fails loudly otherwise.
 """
-from .ocflow import OCflow, ocG, ocOdefun, stepRK1, stepRK4, ocflow_sums, costs_from_sums, invalidate_cache, OCflow_shock   # noqa: F401
+from .ocflow import OCflow, ocG, ocOdefun, stepRK1, stepRK4, ocflow_sums, costs_from_sums, invalidate_cache, OCflow_shock, ocflow_grad_sums, split_param_grads   # noqa: F401
 from .phi import Phi, ResNN   # noqa: F401
 from .problems import Cross2D, SwarmTraj, Quadcopter   # noqa: F401
 from .init_prob import initProb, resample   # noqa: F401
@@ -18,4 +18,4 @@ from .sampler import sample_rho0, resample_device   # noqa: F401
 from . import _cabi   # noqa: F401
 
 __all__ = ["OCflow", "ocG", "ocOdefun", "stepRK1", "stepRK4", "Phi", "ResNN", "Cross2D", "SwarmTraj", "Quadcopter",
-           "initProb", "resample", "OCflow_sharded", "shard_rows", "ocflow_sums", "costs_from_sums", "invalidate_cache", "sample_rho0", "resample_device", "OCflow_shock"]
+           "initProb", "resample", "OCflow_sharded", "shard_rows", "ocflow_sums", "costs_from_sums", "invalidate_cache", "sample_rho0", "resample_device", "OCflow_shock", "ocflow_grad_sums", "split_param_grads"]

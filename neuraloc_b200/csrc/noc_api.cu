@@ -773,6 +773,39 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
 }
 
 template <typename real>
+static int ocflow_grad_impl(const noc_phi_t* ph, const noc_prob_t* pb, const void* x, int64_t n, const double* stage_times,
+                            double t0, double t1, int nt, const double* alph, void* out_costs, void* grad, void* grad_x,
+                            cudaStream_t st) {
+    PhiPack<real> P;
+    PhiRaw<real> R;
+    ProbPack pr;
+    int rc = fill_phi<real>(ph, P, R);
+    if (rc) return rc;
+    rc = check_prob(pb, ph->d, pr);
+    if (rc) return rc;
+    if (ph->nTh != 2) return fail(NOC_ERR_UNSUPPORTED, "noc_ocflow_grad: nTh = %d (the adjoint is written for nTh = 2)", ph->nTh);
+    if (pb->kind == NOC_PROB_QUADCOPTER && pb->nAgents != 1)
+        return fail(NOC_ERR_UNSUPPORTED, "noc_ocflow_grad: Quadcopter with %d agents (one agent only)", pb->nAgents);
+    if (!x || n < 1) return fail(NOC_ERR_ARG, "x is NULL or n < 1");
+    if (nt < 1) return fail(NOC_ERR_ARG, "nt must be >= 1");
+    if (!alph || !out_costs || !grad) return fail(NOC_ERR_ARG, "alph, out_costs or grad is NULL");
+    rc = device_facts();
+    if (rc) return rc;
+    std::vector<double> tab((size_t)nt * 5);
+    if (stage_times) memcpy(tab.data(), stage_times, sizeof(double) * tab.size());
+    else stage_times_host(t0, t1, nt, tab.data());
+    double* dtab = nullptr;
+    NOC_CUDA(cudaMallocAsync((void**)&dtab, sizeof(double) * tab.size(), st));
+    NOC_CUDA(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
+    rc = grad_rollout<real>(ph->d, ph->m, ph->r, (double)P.h, R, pr, (const real*)x, n, dtab, nt, alph, t1, (double*)out_costs,
+                            (real*)grad, (real*)grad_x, g_smem_optin, st);
+    cudaError_t e = cudaFreeAsync(dtab, st);
+    if (rc) return rc;
+    if (e != cudaSuccess) return fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));
+    return NOC_OK;
+}
+
+template <typename real>
 static int phi_eval_impl(const noc_phi_t* ph, const void* s, int64_t n, void* out_phi, void* out_grad, cudaStream_t st, int dtype) {
     RolloutArgs<real> A;
     memset(&A, 0, sizeof A);
@@ -866,6 +899,14 @@ int noc_ocflow_host(const noc_phi_t* phi, const noc_prob_t* prob, const void* x_
     if (dtype == NOC_F64)
         return ocflow_host_impl<double>(phi, prob, x_host, n, stage_times, t0, t1, nt, stepper, alph, mode, out_costs_host,
                                         zFull_host, ctrlFull_host, st, dtype);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
+int noc_ocflow_grad(const noc_phi_t* phi, const noc_prob_t* prob, const void* x, int64_t n, const double* stage_times, double t0,
+                    double t1, int32_t nt, const double* alph, int32_t dtype, void* out_costs, void* grad, void* grad_x, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == NOC_F32) return ocflow_grad_impl<float>(phi, prob, x, n, stage_times, t0, t1, nt, alph, out_costs, grad, grad_x, st);
+    if (dtype == NOC_F64) return ocflow_grad_impl<double>(phi, prob, x, n, stage_times, t0, t1, nt, alph, out_costs, grad, grad_x, st);
     return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
 }
 

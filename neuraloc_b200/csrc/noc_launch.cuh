@@ -50,6 +50,12 @@ int lat_rollout(bool* took, int d, int m, int nTh, int r, double h, const PhiRaw
                 const double* dtimes, int nt, int stepper, int mode, const double* alph, double t_end, double* out_sums,
                 real* out_nomean, real* zFull, real* ctrlFull, int smem_limit, cudaStream_t st);
 
+// training step (noc_grad.cu): rollout + discrete adjoint, tiles of 4 or 8 samples per CTA
+template <typename real>
+int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const ProbPack& pr, const real* x, long long n,
+                 const double* dtimes, int nt, const double* alph, double t_end, double* out_sums, real* grad, real* grad_x,
+                 int smem_limit, cudaStream_t st);
+
 // one translation unit per configuration (noc_inst.cu with -DNOC_CFG_ID=k) defines these
 #define NOC_DECL_LAUNCH(ID, REAL) \
     int launch_cfg_##ID(const RolloutArgs<REAL>& A, const PhiRaw<REAL>* raw, int kmode, size_t smem, cudaStream_t st, double* out_sums);

@@ -195,6 +195,7 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
     __shared__ __align__(8) unsigned long long mbar;
     __shared__ unsigned tmem_base_s, tmem_park_s;
     __shared__ unsigned smax[4];                         // bit patterns of max |K1|, |K0b|, |symb|, |w|
+    __shared__ double sredd[32];                         // 4 sample warps x 8 cost sums of a tile (mean mode)
 
     // ---- one-time per CTA: weights -> scaled, split fp16 operands in canonical layout (padded units have zero weights:
     //      they contribute exactly nothing to any contraction)
@@ -647,14 +648,14 @@ __global__ void __launch_bounds__(SH::NT, SH::MINB) rollout_tc_kernel(const TcAr
             // deterministic CTA sum: lanes -> warp (shuffle tree), warps -> thread 0 in fixed order
 #pragma unroll
             for (int q = 0; q < 7; ++q) {
-                float v = valid ? cost[q] : 0.f;
+                double v = valid ? (double)cost[q] : 0.0;              // double: the sums must not depend on the tiling
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-                if ((tid & 31) == 0 && hf == 0) sred[warp * 8 + q] = v;
+                if ((tid & 31) == 0 && hf == 0) sredd[warp * 8 + q] = v;
             }
             __syncthreads();
             if (tid == 0) {
-                for (int q = 0; q < 7; ++q) csum[q] += (double)sred[q] + (double)sred[8 + q] + (double)sred[16 + q] + (double)sred[24 + q];
+                for (int q = 0; q < 7; ++q) csum[q] += ((sredd[q] + sredd[8 + q]) + sredd[16 + q]) + sredd[24 + q];
                 cnt += nvalid;
             }
             __syncthreads();

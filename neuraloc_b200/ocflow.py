@@ -10,8 +10,10 @@ attributes (class name Cross2D / SwarmTraj / Quadcopter).  The host side only fl
 objects into the C structs of include/noc_b200.h and launches; all arithmetic is in libnoc_b200.so.
 
 Deviations from the reference (documented in DESIGN.md):
-  * forward only — with autograd enabled and parameters (or x) requiring grad this raises instead of
-    silently returning a non-differentiable result (trainOC.py:172 is out of scope);
+  * training (trainOC.py:172-173): with autograd enabled and parameters (or x) requiring grad, the default (mean) return mode
+    with stepper 'rk4' and nTh = 2 runs the fused rollout + discrete-adjoint kernel (noc_ocflow_grad) and `Jc.backward()` works;
+    the gradient flows through Jc only (the entries of cs are detached).  Every other combination raises instead of silently
+    returning a non-differentiable result;
   * errors raise (ValueError / RuntimeError) instead of print + exit(1).
 """
 import ctypes as C
@@ -51,7 +53,7 @@ def _phi_struct(Phi, device, dtype):
     """Flatten the live module into noc_phi_t (device copies in `dtype`; cached until a parameter changes, see
     invalidate_cache)."""
     layers = list(Phi.N.layers)
-    tensors = [Phi.A, Phi.c.weight, Phi.c.bias, Phi.w.weight] + [l.weight for l in layers] + [l.bias for l in layers]
+    tensors = _phi_tensors(Phi)
     sig = tuple((t.data_ptr(), t._version, t.dtype, str(t.device)) for t in tensors)
     per = _PACK_CACHE.setdefault(Phi, {})
     hit = per.get((str(device), dtype))
@@ -105,11 +107,92 @@ def stage_times(t0, t1, nt):
     return tab
 
 
+def _wants_grad(x, Phi):
+    return torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in Phi.parameters()))
+
+
 def _check_forward_only(x, Phi):
-    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in Phi.parameters())):
-        raise RuntimeError("neuraloc_b200.OCflow is forward-only: call it under torch.no_grad() (as evalOC.py / "
-                           "timeOC.py / validation do). Differentiating through the rollout (trainOC.py:172) is not "
-                           "implemented and is never silently approximated.")
+    if _wants_grad(x, Phi):
+        raise RuntimeError("neuraloc_b200: this call is forward-only — run it under torch.no_grad() (as evalOC.py / timeOC.py / "
+                           "validation do). Differentiation is implemented for OCflow's default return mode with stepper='rk4' "
+                           "(trainOC.py:172) and is never silently approximated elsewhere.")
+
+
+def _phi_tensors(Phi):
+    layers = list(Phi.N.layers)
+    return [Phi.A, Phi.c.weight, Phi.c.bias, Phi.w.weight] + [l.weight for l in layers] + [l.bias for l in layers]
+
+
+def ocflow_grad_sums(x, Phi, prob, tspan, nt, alph=(1.0,) * 6, want_xgrad=False):
+    """Training evaluation through noc_ocflow_grad: (sums, grad, grad_x) on the CUDA device —
+    sums   float64 [8] = sums over the rows of x of [L, G, HJt, HJfin, HJgrad, Q, W] and the row count (as ocflow_sums),
+    grad   [P] in x.dtype: SUMS over the rows of d(per-sample objective)/d(parameter), concatenated in state_dict order
+           (A, c.weight, c.bias, w.weight, N.layers.0.weight, N.layers.0.bias, N.layers.1.weight, N.layers.1.bias),
+    grad_x [n, d] or None.  Sums, so that the shards of a multi-GPU batch add (one all-reduce of the two vectors)."""
+    _require_cuda()
+    L = _cabi.lib()
+    if x.dim() != 2:
+        raise ValueError("x must be nex-by-d")
+    code = _dtype_code(x.dtype)
+    n, d = x.shape
+    nt = int(nt)
+    device = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    with torch.cuda.device(device):
+        phi = _phi_struct(Phi, device, x.dtype)
+        if phi.d != d:
+            raise ValueError("x has %d columns but Phi expects d = %d" % (d, phi.d))
+        if phi.nTh != 2:
+            raise RuntimeError("differentiating the rollout is implemented for nTh = 2 (got %d)" % phi.nTh)
+        pst, _keep = _prob_struct(prob, device, x.dtype)
+        tab = stage_times(float(tspan[0]), float(tspan[1]), nt)
+        al = (C.c_double * 6)(*[float(a) for a in alph])
+        xin = x.detach().to(device).contiguous()
+        D, m, r = d + 1, phi.m, phi.r
+        P = r * D + D + 1 + m + m * D + m + m * m + m
+        sums = torch.empty(8, dtype=torch.float64, device=device)
+        grad = torch.empty(P, dtype=x.dtype, device=device)
+        gx = torch.empty(n, d, dtype=x.dtype, device=device) if want_xgrad else None
+        rc = L.noc_ocflow_grad(C.byref(phi), C.byref(pst), xin.data_ptr(), n, tab, float(tspan[0]), float(tspan[1]), nt, al, code,
+                               sums.data_ptr(), grad.data_ptr(), None if gx is None else gx.data_ptr(),
+                               torch.cuda.current_stream(device).cuda_stream)
+        _cabi.check(rc)
+    return sums, grad, gx
+
+
+def split_param_grads(Phi, grad):
+    """The flat gradient of ocflow_grad_sums as tensors shaped like (and ordered as) _phi_tensors(Phi):
+    [A, c.weight, c.bias, w.weight, N.layers.0.weight, N.layers.1.weight, N.layers.0.bias, N.layers.1.bias]."""
+    A, cw, cb, w, K0, K1, b0, b1 = _phi_tensors(Phi)
+    out, off = {}, 0
+    for name, t in (("A", A), ("cw", cw), ("cb", cb), ("w", w), ("K0", K0), ("b0", b0), ("K1", K1), ("b1", b1)):
+        out[name] = grad[off:off + t.numel()].reshape(t.shape)
+        off += t.numel()
+    return [out[k] for k in ("A", "cw", "cb", "w", "K0", "K1", "b0", "b1")]
+
+
+class _RolloutWithAdjoint(torch.autograd.Function):
+    """Jc (differentiable) and the 7 mean cost terms (detached) of one training evaluation; the backward pass only scales the
+    gradient the fused kernel already produced (trainOC.py:172-173)."""
+
+    @staticmethod
+    def forward(ctx, x, Phi, prob, tspan, nt, alph, *params):
+        sums, grad, gx = ocflow_grad_sums(x, Phi, prob, tspan, nt, alph, want_xgrad=x.requires_grad)
+        cnt = sums[7]
+        means = (sums[:7] / cnt).to(x.dtype)
+        Jc = means[0] + alph[0] * means[1] + alph[3] * means[2] + alph[4] * means[3] + alph[5] * means[4]
+        inv = (1.0 / cnt).to(x.dtype)
+        ctx.pgrads = [(g * inv).to(device=p.device, dtype=p.dtype) for g, p in zip(split_param_grads(Phi, grad), params)]
+        ctx.gx = None if gx is None else (gx * inv).to(x.device)
+        ctx.needs = [p.requires_grad for p in params]
+        Jc, means = Jc.to(x.device), means.to(x.device)
+        ctx.mark_non_differentiable(means)
+        return Jc, means
+
+    @staticmethod
+    def backward(ctx, gJ, _gmeans):
+        pg = [(g * gJ.to(g.device)) if need else None for g, need in zip(ctx.pgrads, ctx.needs)]
+        gx = None if ctx.gx is None else ctx.gx * gJ.to(ctx.gx.device)
+        return (gx, None, None, None, None, None, *pg)
 
 
 def _launch(x, Phi, prob, tspan, nt, stepper, alph, mode):
@@ -176,8 +259,11 @@ def OCflow(x, Phi, prob, tspan, nt, stepper="rk4", alph=[1.0, 1.0, 1.0, 1.0, 1.0
              Jc [n,1], cs 7 x [n,1]       with noMean=True (tested first, quirk 4)
              zFull [n,d+4,nt+1], ctrlFull [n,nCtrl,nt+1]   with intermediates=True
     """
-    _check_forward_only(x, Phi)
     alph = [float(a) for a in alph]
+    if _wants_grad(x, Phi) and not noMean and not intermediates and stepper == "rk4":
+        Jc, means = _RolloutWithAdjoint.apply(x, Phi, prob, [float(tspan[0]), float(tspan[1])], int(nt), alph, *_phi_tensors(Phi))
+        return Jc, [means[i] for i in range(7)]
+    _check_forward_only(x, Phi)
     if noMean:
         out = _launch(x, Phi, prob, tspan, nt, stepper, alph, _cabi.MODE_NOMEAN)[0]
         return out[:, 0:1], [out[:, i:i + 1] for i in range(1, 8)]

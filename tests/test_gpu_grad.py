@@ -1,0 +1,112 @@
+"""GPU: the fused rollout + discrete-adjoint kernel (noc_ocflow_grad, trainOC.py:172-173) through the C ABI against reverse-mode
+autograd of the fp64 oracle rollout — what `Jc.backward()` computes in the reference."""
+import dataclasses
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import PROBLEMS, oracle_setup, product_setup
+from test_adjoint_formulas import NAMES, adversarial_batch, autograd_of_oracle
+
+pytestmark = pytest.mark.gpu
+
+ORDER = ["A", "c_w", "c_b", "w", "K0", "K1", "b0", "b1"]          # split_param_grads order
+
+
+def _setup(name, dtype, training):
+    import neuraloc_b200 as nb  # noqa: F401
+    net, prob, xinit, meta = product_setup(name, dtype)
+    (prob.train if training else prob.eval)()
+    P, D, xi64, _ = oracle_setup(name, torch.float64)
+    D = dataclasses.replace(D, training=training)
+    return net, prob, P, D, xi64, meta
+
+
+def _compare(name, dtype, training, n, nt, monkeypatch=None, ts=None):
+    import neuraloc_b200 as nb
+    if ts is not None:
+        monkeypatch.setenv("NOC_GRAD_TS", str(ts))
+    net, prob, P, D, xi64, meta = _setup(name, dtype, training)
+    x64 = adversarial_batch(name, D, xi64, meta["var0"], n)
+    Ja, Ga, xa = autograd_of_oracle(x64, P, D, [0.0, 1.0], nt, meta["alph"])
+    sums, grad, gx = nb.ocflow_grad_sums(x64.to(dtype).cuda(), net, prob, [0.0, 1.0], nt, meta["alph"], want_xgrad=True)
+    with torch.no_grad():
+        Jn, csn = nb.OCflow(x64.to(dtype).cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)
+    assert float(sums[7]) == n
+    al = meta["alph"]
+    Jsum = float(sums[0] + al[0] * sums[1] + al[3] * sums[2] + al[4] * sums[3] + al[5] * sums[4])
+    tolJ, tolg = (1e-10, 1e-8) if dtype == torch.float64 else (2e-5, 5e-3)
+    assert abs(Jsum - float(Ja)) <= tolJ * abs(float(Ja)), (Jsum, float(Ja))
+    assert abs(Jsum - float(Jn.double().sum())) <= tolJ * abs(float(Ja))            # same objective as the forward-only kernels
+    got = dict(zip(ORDER, nb.split_param_grads(net, grad)))
+    worst = {}
+    for k in NAMES:
+        ref = Ga[k]
+        scale = float(ref.abs().max())
+        err = float((got[k].double().cpu().reshape(ref.shape) - ref).abs().max())
+        worst[k] = err / max(scale, 1e-300)
+        assert err <= tolg * max(scale, 1e-30), "%s %s: d/d%s off by %.3e of its largest entry (all: %s)" % (name, dtype, k, worst[k], worst)
+    xerr = float((gx.double().cpu() - xa).abs().max()) / float(xa.abs().max())
+    assert xerr <= tolg, xerr
+    return worst
+
+
+@pytest.mark.parametrize("training", [True, False])
+@pytest.mark.parametrize("name", PROBLEMS)
+def test_grad_fp64_matches_autograd(name, training):
+    n, nt = (6, 3) if name == "swarm50" else (13, 5)
+    _compare(name, torch.float64, training, n, nt)
+
+
+@pytest.mark.parametrize("name", PROBLEMS)
+def test_grad_fp32_matches_autograd(name):
+    n, nt = (6, 3) if name == "swarm50" else (13, 5)
+    _compare(name, torch.float32, True, n, nt)
+
+
+@pytest.mark.parametrize("ts", [4, 8])
+@pytest.mark.parametrize("name", ["swap12", "singlequad", "swarm50"])
+def test_grad_tile_widths(name, ts, monkeypatch):
+    """both tile widths, more tiles than one CTA wave for the narrow nets, a ragged last tile"""
+    n, nt = (21, 2) if name == "swarm50" else (301, 4)
+    _compare(name, torch.float64, True, n, nt, monkeypatch, ts)
+
+
+def test_backward_through_ocflow_like_trainOC():
+    """trainOC.py:169-174: zero_grad, Jc, cs = OCflow(...), Jc.backward(), optimizer step — on the reference-layout module."""
+    import neuraloc_b200 as nb
+    name, nt, n = "softcorridor", 8, 64
+    net, prob, P, D, xi64, meta = _setup(name, torch.float64, True)
+    net.train()
+    x64 = adversarial_batch(name, D, xi64, meta["var0"], n)
+    Ja, Ga, _ = autograd_of_oracle(x64, P, D, [0.0, 1.0], nt, meta["alph"])
+    optim = torch.optim.Adam(net.parameters(), lr=0.01)
+    optim.zero_grad()
+    Jc, cs = nb.OCflow(x64.cuda(), net, prob, tspan=[0.0, 1.0], nt=nt, stepper="rk4", alph=meta["alph"])
+    assert Jc.requires_grad and not cs[0].requires_grad
+    Jc.backward()
+    assert abs(float(Jc) - float(Ja) / n) <= 1e-10 * abs(float(Ja) / n)
+    named = {"A": net.A, "c_w": net.c.weight, "c_b": net.c.bias, "w": net.w.weight, "K0": net.N.layers[0].weight,
+             "K1": net.N.layers[1].weight, "b0": net.N.layers[0].bias, "b1": net.N.layers[1].bias}
+    for k, p in named.items():
+        ref = Ga[k] / n
+        assert p.grad is not None and p.grad.shape == p.shape
+        assert float((p.grad.cpu().reshape(ref.shape) - ref).abs().max()) <= 1e-8 * max(float(ref.abs().max()), 1e-30), k
+    before = net.N.layers[1].weight.detach().clone()
+    optim.step()
+    assert not torch.equal(before, net.N.layers[1].weight.detach())
+    # the next evaluation sees the updated weights (the packed-weight cache is keyed on the parameter versions)
+    with torch.no_grad():
+        J2, _ = nb.OCflow(x64.cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"])
+    assert float(J2) != float(Jc)
+
+
+def test_grad_modes_that_are_not_differentiable_raise():
+    import neuraloc_b200 as nb
+    net, prob, P, D, xi64, meta = _setup("softcorridor", torch.float32, True)
+    x = xi64.float().cuda().repeat(4, 1)
+    with pytest.raises(RuntimeError):
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"], noMean=True)
+    with pytest.raises(RuntimeError):
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk1", meta["alph"])

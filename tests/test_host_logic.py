@@ -101,8 +101,13 @@ def test_descriptor_flattening_and_guards():
     with torch.no_grad():
         net.w.weight.add_(1.0)
     assert ocflow._phi_struct(net, torch.device("cpu"), torch.float64) is not ph      # invalidated by a parameter update
+    with pytest.raises(RuntimeError, match="forward-only"):          # noMean / intermediates / rk1 are not differentiable: loud
+        nb.OCflow(xinit, net, prob, [0.0, 1.0], 4, noMean=True)
     with pytest.raises(RuntimeError, match="forward-only"):
-        nb.OCflow(xinit, net, prob, [0.0, 1.0], 4)
+        nb.OCflow(xinit, net, prob, [0.0, 1.0], 4, "rk1")
+    if not torch.cuda.is_available():                                # the training path needs the GPU like everything else
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            nb.OCflow(xinit, net, prob, [0.0, 1.0], 4)
     class Weird:
         pass
     with pytest.raises(ValueError):
