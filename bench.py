@@ -320,6 +320,87 @@ def intermediates_mode(args, W, dtype):
                          "note": "peak = MEASURED_PEAKS.json hbm_gbs (copy: read + write); algorithmic bytes = the two output tensors, written once"}}
 
 
+# the reference's own training commands (README.md:103-123): batch size and time steps of one trainOC.py iteration
+TRAIN = {"softcorridor": (1024, 20), "swap2": (1024, 20), "swap12": (2048, 20), "swarm50": (1024, 26), "singlequad": (1024, 26),
+         "config5": (1024, 26)}
+
+
+def train_mode(args, W, dtype, threads):
+    """One training evaluation, trainOC.py:169-173: Jc, cs = OCflow(x0, net, prob, ...) in train mode, then Jc.backward() —
+    here ONE fused kernel (forward sweep + discrete adjoint, noc_ocflow_grad) behind the same two Python calls.  Batch size and
+    nt are those of the reference's README training commands.  CPU arm: autograd through the oracle port on all host threads."""
+    import neuraloc_b200 as nb
+    nb._cabi.lib()
+    torch.cuda.set_device(0)
+    device = torch.device("cuda", 0)
+    n, nt = TRAIN[args.workload]
+    n = args.n or n
+    net, prob, xinit, meta = build_case(args.workload, device, dtype)
+    prob.train(); net.train()
+    x = sample_x(args.workload, xinit, meta["var0"], n, 1234, device, dtype)
+    params = list(net.parameters())
+
+    def iteration():
+        for p in params:
+            p.grad = None
+        Jc, cs = nb.OCflow(x, net, prob, [0.0, 1.0], nt, "rk4", meta["alph"])
+        Jc.backward()
+        return Jc
+    for _ in range(max(3, args.warmup)):
+        Jc = iteration()
+    torch.cuda.synchronize()
+    before = nb._cabi.launch_count()
+    ms = []
+    for _ in range(args.steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        Jc = iteration()
+        e1.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e1))
+    launches = nb._cabi.launch_count() - before
+    t = statistics.mean(ms) * 1e-3
+    gnorm = float(torch.sqrt(sum((p.grad.double() ** 2).sum() for p in params)))
+    # forward flops (SURVEY 8d) x (1 forward + 4 stages re-evaluated with 8 instead of 4 contractions + 4 rank-TS updates)
+    d, m = x.shape[1], meta["m"]
+    fl = flops_per_sample_step(d, m, 2, min(10, d + 1))
+    line = {"metric": "train_sample_steps_per_sec", "value": n * nt / t, "unit": "sample-steps/s (forward + backward)", "n_gpus": 1,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": statistics.mean(ms), "higher_is_better": True,
+            "dtype": W["dtype"], "data": "synthetic",
+            "config": {"workload": "%s, one trainOC.py iteration (OCflow in train mode + Jc.backward()), n_train=%d, nt=%d "
+                                   "(README.md:103-123), x ~ xInit + var0*N(0,I)" % (args.workload, n, nt),
+                       "Jc": float(Jc), "grad_norm": gnorm},
+            "gpu_launches": launches,
+            "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "unit": "TFLOP/s",
+                         "achieved": 4.0 * fl * n * nt / t / 1e12,
+                         "note": "algorithmic flops of forward + adjoint = 4 x the forward's (8 instead of 4 contractions per "
+                                 "re-evaluated stage + the parameter-gradient outer products) / time; FMA kernel"}}
+    if not args.no_cpu_baseline:
+        from oracle import ocflow_oracle as orc
+        import dataclasses
+        torch.set_num_threads(threads)
+        sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        P = orc.params_from_state_dict(sd, dtype)
+        D, _ = orc.make_problem(meta["data"], meta["alph"], dtype)
+        D = dataclasses.replace(D, training=True)
+        leaves = [t.clone().requires_grad_(True) for t in (P.A, P.c_w, P.c_b, P.w, P.K[0], P.K[1], P.b[0], P.b[1])]
+        Pg = orc.PhiParams(leaves[0], leaves[1], leaves[2], leaves[3], [leaves[4], leaves[5]], [leaves[6], leaves[7]], P.h)
+        xc = x.cpu()
+        best, Jr = 1e30, None
+        for _ in range(2):
+            for t_ in leaves:
+                t_.grad = None
+            t0 = time.perf_counter()
+            Jr, _ = orc.ocflow(xc, Pg, D, [0.0, 1.0], nt, "rk4", meta["alph"])
+            Jr.backward()
+            best = min(best, time.perf_counter() - t0)
+        gn = float(torch.sqrt(sum((t_.grad.double() ** 2).sum() for t_ in leaves)))
+        line["cpu_baseline"] = {"value": n * nt / best, "unit": "sample-steps/s (forward + backward)", "cores": threads, "kind": "port",
+                                "ms_per_iteration": best * 1e3, "Jc": float(Jr), "grad_norm": gn,
+                                "sample": "the same batch (n=%d, nt=%d), torch autograd through the oracle port, best of 2" % (n, nt)}
+    return line
+
+
 def measure(workload, n, steps, warmup, device, dtype, dist, rank, world, seed_rank, want_clocks, e2e_steps):
     """Device-timed rollout steps over this rank's n samples (+ the e2e leg with host buffers).  Returns a dict of raw numbers."""
     import neuraloc_b200 as nb
@@ -412,6 +493,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the swap12 / singlequad full-size extra lines")
     ap.add_argument("--latency", action="store_true", help="batch-1 rollout latency (timeDeployment/timeOC.py protocol) instead of throughput")
+    ap.add_argument("--train", action="store_true", help="time one training evaluation: OCflow in train mode + Jc.backward() (SURVEY.md 8f N1)")
     ap.add_argument("--intermediates", action="store_true", help="time OCflow(..., intermediates=True): trajectories + controls written to HBM (SURVEY.md 8f N2)")
     args = ap.parse_args()
     W = WORKLOADS[args.workload]
@@ -449,6 +531,9 @@ def main():
         return
     if args.intermediates:
         print(json.dumps(intermediates_mode(args, W, dtype)))
+        return
+    if args.train:
+        print(json.dumps(train_mode(args, W, dtype, threads)))
         return
 
     # ------------------------------------------------------------------ our arm

@@ -70,7 +70,8 @@ def test_grad_fp32_matches_autograd(name):
 def test_grad_tile_widths(name, ts, monkeypatch):
     """both tile widths, more tiles than one CTA wave for the narrow nets, a ragged last tile"""
     n, nt = (21, 2) if name == "swarm50" else (301, 4)
-    _compare(name, torch.float64, True, n, nt, monkeypatch, ts)
+    fits64 = not (name == "swarm50" and ts == 8)          # 8-sample fp64 panels of the m = 512 net exceed shared memory
+    _compare(name, torch.float64 if fits64 else torch.float32, True, n, nt, monkeypatch, ts)
 
 
 def test_backward_through_ocflow_like_trainOC():
