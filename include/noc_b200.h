@@ -192,6 +192,21 @@ int noc_ocflow_grad(const noc_phi_t* phi, const noc_prob_t* prob, const void* x,
                     const double* stage_times, double t0, double t1, int32_t nt, const double* alph, int32_t dtype,
                     void* out_costs, void* grad, void* grad_x, void* stream);
 
+/*
+ * noc_baseline_loss — replaces the baseline's discrete-control objective for a batch of initial states:
+ * loss_fun(U, Z_0, prob, nt, alphG) (baseline2D.py:42-63, timeBaseline.py:50-70; Cross2D / SwarmTraj problems:
+ * Z += h U_i, loss += h L(Z, U_i) with L from calcLHQW, + alphG G(Z_nt)) and compute_loss(ctrls, x0, prob, alphG) with dyn
+ * (baselineQuad.py:40-72; one quadcopter: x += h dyn(c_i, x), J += h (2 + |c_i|^2), + alphG 0.5 |x - xtarget|^2), h = 1/nt,
+ * and — when gradU is not NULL — `err.backward()` of the optimisation loops (baseline2D.py:97-102, baselineQuad.py:80-86).
+ * The reference evaluates one initial state per Python call; here every sample of the batch is one warp of one launch.
+ *   U      dev [n, nt, nc]   controls, nc = d (Cross2D, SwarmTraj) or 4 (Quadcopter: thrust, three torques)
+ *   z0     dev [n, d]        initial states
+ *   loss   dev [n]           per-sample objective
+ *   gradU  dev [n, nt, nc] or NULL: d loss[i] / d U[i]
+ */
+int noc_baseline_loss(const noc_prob_t* prob, const void* U, const void* z0, int64_t n, int32_t d, int32_t nt, double alphG,
+                      int32_t dtype, void* loss, void* gradU, void* stream);
+
 /* Which kernel family the calling thread's last noc_ocflow / noc_ocflow_host call ran (-1 before the first call):
  * the FMA sample-tile kernel, the one-CTA-per-sample small-batch kernel, or the tensor-core kernel.  The choice is made
  * from the shapes and the batch size; env NOC_TC=0 disables the tensor-core kernel, NOC_FORCE_PATH=tile|vec|tc pins one. */

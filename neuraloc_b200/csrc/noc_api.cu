@@ -910,6 +910,22 @@ int noc_ocflow_grad(const noc_phi_t* phi, const noc_prob_t* prob, const void* x,
     return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
 }
 
+int noc_baseline_loss(const noc_prob_t* prob, const void* U, const void* z0, int64_t n, int32_t d, int32_t nt, double alphG,
+                      int32_t dtype, void* loss, void* gradU, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    ProbPack pr;
+    int rc = check_prob(prob, d, pr);
+    if (rc) return rc;
+    if (!U || !z0 || !loss || n < 1 || nt < 1) return fail(NOC_ERR_ARG, "U, z0 or loss is NULL, or n < 1, or nt < 1");
+    if (prob->kind == NOC_PROB_QUADCOPTER && prob->nAgents != 1)
+        return fail(NOC_ERR_UNSUPPORTED, "noc_baseline_loss: Quadcopter with %d agents (baselineQuad.py handles one)", prob->nAgents);
+    rc = device_facts();
+    if (rc) return rc;
+    if (dtype == NOC_F32) return baseline_loss<float>(pr, (const float*)U, (const float*)z0, n, d, nt, alphG, (float*)loss, (float*)gradU, st);
+    if (dtype == NOC_F64) return baseline_loss<double>(pr, (const double*)U, (const double*)z0, n, d, nt, alphG, (double*)loss, (double*)gradU, st);
+    return fail(NOC_ERR_ARG, "dtype must be NOC_F32 or NOC_F64");
+}
+
 int noc_phi_eval(const noc_phi_t* phi, const void* s, int64_t n, int32_t dtype, void* out_phi, void* out_grad, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (dtype == NOC_F32) return phi_eval_impl<float>(phi, s, n, out_phi, out_grad, st, dtype);

@@ -56,6 +56,11 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
                  const double* dtimes, int nt, const double* alph, double t_end, double* out_sums, real* grad, real* grad_x,
                  int smem_limit, cudaStream_t st);
 
+// baseline objective (noc_baseline.cu): one warp per sample
+template <typename real>
+int baseline_loss(const ProbPack& pr, const real* U, const real* z0, long long n, int d, int nt, double alphG, real* loss, real* gradU,
+                  cudaStream_t st);
+
 // one translation unit per configuration (noc_inst.cu with -DNOC_CFG_ID=k) defines these
 #define NOC_DECL_LAUNCH(ID, REAL) \
     int launch_cfg_##ID(const RolloutArgs<REAL>& A, const PhiRaw<REAL>* raw, int kmode, size_t smem, cudaStream_t st, double* out_sums);

@@ -13,6 +13,7 @@ What it restates (reference = donken/NeuralOC, read-only at /root/reference in t
   rk4_step / rk1_step      src/OCflow.py:157-184, 143-155
   ocflow                   src/OCflow.py:7-95
   make_problem             src/initProb.py:9-249 (targets / initial centres / radii)
+  baseline_loss            baseline2D.py:42-63 (loss_fun), baselineQuad.py:40-72 (dyn, compute_loss), batched over samples
 
 The arithmetic lives in PyTorch (CPU aten kernels; the reference pins torch==1.7.0, this image has
 2.11): this file is a functional restatement on plain tensors (no nn.Module, no problem classes), in
@@ -32,7 +33,7 @@ from typing import List, Optional, Sequence
 import torch
 
 __all__ = ["PhiParams", "ProbDesc", "phi_forward", "phi_grad", "lhqw", "grad_p_hamiltonian", "controls",
-           "rhs", "ocflow", "stage_time_table", "make_problem", "params_from_state_dict"]
+           "rhs", "ocflow", "stage_time_table", "make_problem", "params_from_state_dict", "baseline_loss"]
 
 
 # ----------------------------------------------------------------------------------------------
@@ -388,6 +389,36 @@ def ocflow(x, P: PhiParams, D: ProbDesc, tspan: Sequence[float], nt: int, steppe
     if intermediates:
         return zfull, cfull
     return cs[0] + alph[0] * cs[1] + alph[3] * cs[2] + alph[4] * cs[3] + alph[5] * cs[4], cs
+
+
+# ----------------------------------------------------------------------------------------------
+# baseline: discrete-control objective
+# ----------------------------------------------------------------------------------------------
+def baseline_loss(D: ProbDesc, U, z0, alphG: float):
+    """Per-sample objective of the baseline method for controls U [n, nt, nc] and initial states z0 [n, d] -> [n].
+
+    Cross2D / SwarmTraj — loss_fun, baseline2D.py:42-63: Z += h U_i; loss += h L(Z, U_i) (L of calcLHQW with p := U_i, at the
+    NEW state); + alphG * 0.5 |Z_nt - xtarget|^2.  Quadcopter — dyn / compute_loss, baselineQuad.py:40-72: x += h dyn(c_i, x)
+    with dyn = [x[6:], (c0/mass) f(x[3:6]) - grav e_z, c[1:4]]; J += h (2 + |c_i|^2); + alphG * 0.5 |x_nt - xtarget|^2."""
+    n, nt = U.shape[0], U.shape[1]
+    h = 1.0 / nt
+    Z = z0
+    loss = torch.zeros(n, dtype=U.dtype)
+    if D.kind == "Quadcopter":
+        for i in range(nt):
+            c = U[:, i, :]
+            f7, f8, f9 = _quad_f(Z[:, 3:6])
+            tmp = c[:, 0] / D.mass
+            dx = torch.cat([Z[:, 6:], (tmp * f7).unsqueeze(1), (tmp * f8).unsqueeze(1), (tmp * f9 - D.grav).unsqueeze(1), c[:, 1:4]], 1)
+            Z = Z + h * dx
+            loss = loss + h * (2 + torch.norm(c, p=2, dim=1) ** 2)
+        return loss + alphG * 0.5 * torch.norm(Z - D.xtarget, p=2, dim=1) ** 2
+    for i in range(nt):
+        Z = Z + h * U[:, i, :]
+        L = lhqw(D, Z, U[:, i, :])[0]
+        loss = loss + h * L.reshape(-1)
+    cG = 0.5 * torch.sum((Z - D.xtarget) ** 2, 1)
+    return loss + alphG * cG
 
 
 # ----------------------------------------------------------------------------------------------
