@@ -13,10 +13,10 @@ from .ocflow import OCflow, ocG, ocOdefun, stepRK1, stepRK4, ocflow_sums, costs_
 from .phi import Phi, ResNN   # noqa: F401
 from .problems import Cross2D, SwarmTraj, Quadcopter   # noqa: F401
 from .init_prob import initProb, resample   # noqa: F401
-from .sharded import OCflow_sharded, shard_rows   # noqa: F401
+from .sharded import OCflow_sharded, shard_rows, ocflow_grad_sharded   # noqa: F401
 from .sampler import sample_rho0, resample_device   # noqa: F401
 from .baseline import baseline_loss, loss_fun, compute_loss   # noqa: F401
 from . import _cabi   # noqa: F401
 
 __all__ = ["OCflow", "ocG", "ocOdefun", "stepRK1", "stepRK4", "Phi", "ResNN", "Cross2D", "SwarmTraj", "Quadcopter",
-           "initProb", "resample", "OCflow_sharded", "shard_rows", "ocflow_sums", "costs_from_sums", "invalidate_cache", "sample_rho0", "resample_device", "OCflow_shock", "ocflow_grad_sums", "split_param_grads", "baseline_loss", "loss_fun", "compute_loss"]
+           "initProb", "resample", "OCflow_sharded", "shard_rows", "ocflow_sums", "costs_from_sums", "invalidate_cache", "sample_rho0", "resample_device", "OCflow_shock", "ocflow_grad_sums", "split_param_grads", "baseline_loss", "loss_fun", "compute_loss", "ocflow_grad_sharded"]

@@ -7,7 +7,7 @@ collective; the only exchange is one all-reduce (sum) of the 8-double vector
 """
 import torch
 
-from .ocflow import costs_from_sums, ocflow_sums
+from .ocflow import costs_from_sums, ocflow_grad_sums, ocflow_sums, split_param_grads, _phi_tensors
 
 
 def shard_rows(n, world_size, rank):
@@ -36,3 +36,38 @@ def OCflow_sharded(x_local, Phi, prob, tspan, nt, stepper="rk4", alph=(1.0,) * 6
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
     return costs_from_sums(sums, alph, x_local.dtype)
+
+
+def ocflow_grad_sharded(x_local, Phi, prob, tspan, nt, alph=(1.0,) * 6, group=None, local_eval=None, assign=True):
+    """Data-parallel training evaluation (trainOC.py:172-173 over the union of every rank's rows): each rank runs the fused
+    rollout + adjoint kernel on its own rows, and ONE all-reduce (sum) of the float64 vector [8 cost sums | P parameter-gradient
+    sums] follows; every rank then holds the same Jc, cs and mean gradient.  With `assign` the gradients are written to the
+    parameters' `.grad` (replacing them), so that `optim.step()` can follow as in the reference's loop.
+
+    `local_eval(x, Phi, prob, tspan, nt, alph) -> (sums [8], grad [P])` lets the host logic run without a GPU (tests inject
+    autograd through the CPU oracle); the default is noc_ocflow_grad.  Returns (Jc, cs, grads) with grads ordered like
+    [A, c.weight, c.bias, w.weight, N.layers.0.weight, N.layers.1.weight, N.layers.0.bias, N.layers.1.bias]."""
+    import torch.distributed as dist
+    alph = [float(a) for a in alph]
+    params = _phi_tensors(Phi)
+    P = sum(p.numel() for p in params)
+    dev = x_local.device
+    if x_local.shape[0] > 0:
+        if local_eval is not None:
+            sums, grad = local_eval(x_local, Phi, prob, tspan, nt, alph)
+        else:
+            sums, grad, _ = ocflow_grad_sums(x_local, Phi, prob, tspan, nt, alph)
+        dev = sums.device
+        buf = torch.cat((sums.to(torch.float64), grad.to(torch.float64)))
+    else:
+        if local_eval is None:
+            dev = torch.device("cuda", torch.cuda.current_device())
+        buf = torch.zeros(8 + P, dtype=torch.float64, device=dev)
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM, group=group)
+    Jc, cs = costs_from_sums(buf[:8], alph, x_local.dtype)
+    grads = split_param_grads(Phi, (buf[8:] / buf[7]).to(x_local.dtype))
+    if assign:
+        for p, g in zip(params, grads):
+            p.grad = g.to(device=p.device, dtype=p.dtype).clone()
+    return Jc, cs, grads
