@@ -16,7 +16,7 @@ public API with HOST (pinned) buffers, copies inside the timed region; `roofline
 its roof (tensor kernels: executed MMA flops / MEASURED_PEAKS.json bf16 peak, with the algorithmic fp32 rate / live-measured
 FMA peak alongside; FMA kernels: algorithmic flops / live-measured FMA peak); `cpu_baseline` = the CPU oracle port (torch CPU,
 all host threads) on a bounded sample of the same workload; `extra` = the full-size configs[1] (swap12, 2^20) and configs[2]
-(singlequad, 2^22) lines, N = 1 only.
+(singlequad, 2^22) lines and two training-iteration lines (`--train`), N = 1 only.
 `--impl reference` times only the CPU arm (the reference is pure Python/torch and cannot travel to the GPU box;
 oracle/ocflow_oracle.py is its restatement, pinned against the reference's outputs in tests/).
 """
@@ -621,6 +621,14 @@ def main():
                              "clocks": me["clocks"], "Jc": Je,
                              "roofline": roofline(wl, We, me["d"], me["meta"], We["n"], We["nt"], fle, statistics.mean(me["step_ms"]) * 1e-3,
                                                   peak, me["path"], me["clocks"])}
+            # one trainOC.py iteration (forward + backward) at the reference's training shapes
+            class _A:
+                pass
+            for wl in ("swarm50", "softcorridor"):
+                ta = _A()
+                ta.workload, ta.n, ta.steps, ta.warmup, ta.no_cpu_baseline = wl, 0, 5, 3, (wl != "swarm50")
+                tl = train_mode(ta, WORKLOADS[wl], torch.float32, threads)
+                extra["train_" + wl] = {k: tl[k] for k in ("metric", "value", "unit", "ms_per_step", "config", "gpu_launches", "roofline", "cpu_baseline") if k in tl}
             line["extra"] = extra
         print(json.dumps(line))
     if dist is not None:

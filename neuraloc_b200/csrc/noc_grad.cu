@@ -117,6 +117,20 @@ __device__ __forceinline__ real sgn(real v) { return real((v > real(0)) - (v < r
 
 template <typename real>
 __device__ __forceinline__ void red_add(real* p, real v) { atomicAdd(p, v); }   // result unused: RED.E.ADD
+// four consecutive floats (16-byte aligned) in one reduction: REDG.E.ADD.F32x4
+__device__ __forceinline__ void red_add4(float* p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// gradient sections: accumulation buffer (every section 16-byte aligned, so that rows of K1 take vector reductions) -> the
+// caller's compact state_dict-order vector
+struct GradSections { int src[8], dst[8], len[8]; };
+template <typename real>
+__global__ void unpack_grad_kernel(const real* __restrict__ acc, real* __restrict__ out, const GradSections S) {
+    const int stride = gridDim.x * blockDim.x, t0 = blockIdx.x * blockDim.x + threadIdx.x;
+    for (int q = 0; q < 8; ++q)
+        for (int i = t0; i < S.len[q]; i += stride) out[S.dst[q] + i] = acc[S.src[q] + i];
+}
 
 // out_j[.] = sum_k W[k*N + j] in[k][.]  for the N outputs; epi(j, acc) runs in the thread that owns output j (j = tid, tid+NT, ...).
 // nsplit > 1: the K range is cut into nsplit slices worked on by thread groups of NT / nsplit threads (for N << NT); the partial
@@ -130,6 +144,20 @@ __device__ __forceinline__ void matvec(const real* __restrict__ W, int N, int K,
         for (int s = 0; s < TS; ++s) acc[s] = real(0);
         const real* wp = W + j;
         int k = kb;
+        // eight weight loads in flight per thread before their FMAs: a weight element is used by ONE thread (TS FMAs), so the
+        // loop is bound by how many bytes the SM keeps in flight towards L2, not by the FMA pipe
+        for (; k + 8 <= ke; k += 8) {
+            real w8[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) w8[u] = ldw(wp + (size_t)(k + u) * N);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                real a[TS];
+                ld_row<real, TS>(in + (k + u) * TS, a);
+#pragma unroll
+                for (int s = 0; s < TS; ++s) acc[s] = r_fma(w8[u], a[s], acc[s]);
+            }
+        }
         for (; k + 2 <= ke; k += 2) {
             real w0 = ldw(wp + (size_t)k * N), w1 = ldw(wp + (size_t)(k + 1) * N);
             real a[TS], b[TS];
@@ -432,20 +460,48 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
             as_[i] = a1; ag_[i] = a2;
         }
         __syncthreads();
-        // dK1[j][k] += h w_j sum_s T1[j][s] udot[k][s] + sum_s bar_a1[j][s] u0[k][s]      (thread = column k: coalesced reds)
-        for (int k = tid; k < m; k += NT) {
-            real ud[TS], uu[TS];
-            ld_row<real, TS>(X1 + k * TS, ud);
-            ld_row<real, TS>(u0 + k * TS, uu);
-            real* gk = A.grad + P.g_K1 + k;
-            for (int j = 0; j < m; ++j) {
-                real t[TS], b[TS];
-                ld_row<real, TS>(T1 + j * TS, t);
-                ld_row<real, TS>(AD + j * TS, b);
-                real a1 = real(0), a2 = real(0);
+        // dK1[j][k] += h w_j sum_s T1[j][s] udot[k][s] + sum_s bar_a1[j][s] u0[k][s]
+        if (sizeof(real) == 4 && (m & 3) == 0 && (NT % (m / 4) == 0 || NT < m / 4)) {
+            // fp32: a thread owns FOUR consecutive columns k (its udot / u0 rows in registers) for a slice of the rows j; one
+            // 16-byte vector reduction per row (REDG.ADD.F32x4, coalesced over the column groups) and 64 FMAs per pair of row loads
+            const int KG = m >> 2, nrg = (NT >= KG) ? NT / KG : 1;
+            for (int kg = tid % KG, rg = tid / KG; kg < KG && rg < nrg; kg += NT) {      // NT < KG: column groups in passes
+                real ud[4][TS], uu[4][TS];
 #pragma unroll
-                for (int q = 0; q < TS; ++q) { a1 = r_fma(t[q], ud[q], a1); a2 = r_fma(b[q], uu[q], a2); }
-                red_add(gk + (size_t)j * m, r_fma(h * Ww[j], a1, a2));
+                for (int c = 0; c < 4; ++c) { ld_row<real, TS>(X1 + (4 * kg + c) * TS, ud[c]); ld_row<real, TS>(u0 + (4 * kg + c) * TS, uu[c]); }
+                const int jb = (m * rg) / nrg, je = (m * (rg + 1)) / nrg;
+                float* gk = reinterpret_cast<float*>(A.grad) + P.g_K1 + 4 * kg;
+                for (int j = jb; j < je; ++j) {
+                    real t[TS], b[TS];
+                    ld_row<real, TS>(T1 + j * TS, t);
+                    ld_row<real, TS>(AD + j * TS, b);
+                    const real hw = h * Ww[j];
+                    float o[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        real a1 = real(0), a2 = real(0);
+#pragma unroll
+                        for (int q = 0; q < TS; ++q) { a1 = r_fma(t[q], ud[c][q], a1); a2 = r_fma(b[q], uu[c][q], a2); }
+                        o[c] = (float)r_fma(hw, a1, a2);
+                    }
+                    red_add4(gk + (size_t)j * m, o[0], o[1], o[2], o[3]);
+                }
+            }
+        } else {                                                                       // thread = column k: coalesced scalar reds
+            for (int k = tid; k < m; k += NT) {
+                real ud[TS], uu[TS];
+                ld_row<real, TS>(X1 + k * TS, ud);
+                ld_row<real, TS>(u0 + k * TS, uu);
+                real* gk = A.grad + P.g_K1 + k;
+                for (int j = 0; j < m; ++j) {
+                    real t[TS], b[TS];
+                    ld_row<real, TS>(T1 + j * TS, t);
+                    ld_row<real, TS>(AD + j * TS, b);
+                    real a1 = real(0), a2 = real(0);
+#pragma unroll
+                    for (int q = 0; q < TS; ++q) { a1 = r_fma(t[q], ud[q], a1); a2 = r_fma(b[q], uu[q], a2); }
+                    red_add(gk + (size_t)j * m, r_fma(h * Ww[j], a1, a2));
+                }
             }
         }
         // dK0[j][c] += sum_s v[j][s] gbar[c][s] + bar_o[j][s] s[c][s]                      (thread = column c, rows in slices)
@@ -638,8 +694,10 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     P.off_W1t = take(D * m); P.off_Kft = take(m * m); P.off_Kr = take(m * m); P.off_W4 = take(m * D); P.off_sym = take(D * D);
     P.off_b0 = take(m); P.off_b1 = take(m); P.off_w = take(m); P.off_cw = take(D); P.off_cb = take(1); P.off_A = take(r * D);
     P.blob_len = off;
-    int go = 0;
-    auto gtake = [&](int cnt) { int o = go; go += cnt; return o; };
+    // the kernel accumulates into a buffer whose sections start on 16-byte boundaries; unpack_grad_kernel compacts it
+    GradSections GS;
+    int go = 0, co = 0, gi = 0;
+    auto gtake = [&](int cnt) { int o = go; GS.src[gi] = go; GS.dst[gi] = co; GS.len[gi] = cnt; ++gi; go += align_up(cnt, 4); co += cnt; return o; };
     P.g_A = gtake(r * D); P.g_cw = gtake(D); P.g_cb = gtake(1); P.g_w = gtake(m); P.g_K0 = gtake(m * D); P.g_b0 = gtake(m);
     P.g_K1 = gtake(m * m); P.g_b1 = gtake(m); P.g_len = go;
 
@@ -682,11 +740,13 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     P.blob = blob;
     NOC_CUDA(cudaMallocAsync((void**)&xsave, sizeof(real) * (size_t)A.ntiles * nt * 4 * d * TS, st));
     NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)A.ntiles, st));
-    NOC_CUDA(cudaMemsetAsync(grad, 0, sizeof(real) * (size_t)P.g_len, st));
+    real* gacc = nullptr;
+    NOC_CUDA(cudaMallocAsync((void**)&gacc, sizeof(real) * (size_t)P.g_len, st));
+    NOC_CUDA(cudaMemsetAsync(gacc, 0, sizeof(real) * (size_t)P.g_len, st));
     A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.times = dtimes;
     A.alph0 = (real)alph[0]; A.alph3 = (real)alph[3]; A.alph4 = (real)alph[4]; A.alph5 = (real)alph[5];
     A.t_end = (real)t_end;
-    A.partials = partials; A.grad = grad; A.grad_x = grad_x; A.xsave = xsave;
+    A.partials = partials; A.grad = gacc; A.grad_x = grad_x; A.xsave = xsave;
     void (*kern)(const GradArgs<real>) = nullptr;
     if (TS == 8) kern = wsm ? rollout_grad_kernel<real, 8, true> : rollout_grad_kernel<real, 8, false>;
     else kern = wsm ? rollout_grad_kernel<real, 4, true> : rollout_grad_kernel<real, 4, false>;
@@ -698,8 +758,12 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     kern<<<grid, NT, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
+    unpack_grad_kernel<real><<<std::min(std::max(1, ceil_div(P.g_len, 256)), 4 * sm_count()), 256, 0, st>>>(gacc, grad, GS);
+    count_launch();
+    NOC_CUDA(cudaGetLastError());
     int frc = launch_finish(partials, A.ntiles, out_sums, st);
     if (frc) return frc;
+    NOC_CUDA(cudaFreeAsync(gacc, st));
     NOC_CUDA(cudaFreeAsync(partials, st));
     NOC_CUDA(cudaFreeAsync(xsave, st));
     NOC_CUDA(cudaFreeAsync(blob, st));
