@@ -27,6 +27,8 @@
 // The L / HJt accumulators of z have constant adjoints (1 and alpha_3), Q and W are reported only (adjoint 0), so the only state
 // adjoint is lambda = dJ/dx, a [d][TS] panel.
 #include "noc_launch.cuh"
+#include <cstdio>
+#include <cstdlib>
 #include "noc_adjoint.cuh"
 
 namespace noc {
@@ -61,6 +63,8 @@ struct GradArgs {
     real* grad_x;              // [n][d] or NULL
     real* xsave;               // [ntiles][nt][4][d][TS]
     int nsplitD;               // K-slices of the D-wide contractions (K0'v, K0'bar_o)
+    int precise;               // experiment switch: libm activation pair
+    int use_v4, deep;          // experiment switches: vector reductions for dK1, eight weight loads in flight
     // shared-memory offsets (elements)
     int o_s, o_g, o_gb, o_q, o_sb, o_xd, o_lam, o_xbn, o_xsum, o_z0, o_za, o_sc, o_red, o_qx, o_as, o_ag, o_bt, o_vm, o_part;
     int o_T0, o_u0, o_T1, o_z1, o_od, o_ad, o_x1, o_x2, o_w;
@@ -112,6 +116,15 @@ __device__ __forceinline__ void ld_row(const real* p, real (&v)[TS]) {
     }
 }
 
+// libm variants of the activation pair (experiment switch NOC_GRAD_PRECISE=1; the default is the MUFU pair of noc_rollout.cuh)
+template <typename real>
+__device__ __forceinline__ void act_tanh_sel(bool precise, real pre, real& av, real& tv) {
+    if (!precise) { act_tanh(pre, av, tv); return; }
+    const real a = r_abs(pre);
+    if constexpr (sizeof(real) == 4) { const float e = expf(-2.f * a); av = a + log1pf(e); tv = copysignf((1.f - e) / (1.f + e), pre); }
+    else { const double e = exp(-2.0 * a); av = a + log1p(e); tv = copysign((1.0 - e) / (1.0 + e), pre); }
+}
+
 template <typename real>
 __device__ __forceinline__ real sgn(real v) { return real((v > real(0)) - (v < real(0))); }
 
@@ -137,7 +150,7 @@ __global__ void unpack_grad_kernel(const real* __restrict__ acc, real* __restric
 // sums meet in `part` ([nsplit][N][TS]).  Every thread of the CTA must call; the caller synchronises before the outputs are read.
 template <typename real, int TS, bool WSM, class Epi>
 __device__ __forceinline__ void matvec(const real* __restrict__ W, int N, int K, const real* in, real* part, int nsplit,
-                                       int tid, int NT, Epi epi) {
+                                       int tid, int NT, bool deep, Epi epi) {
     auto ldw = [](const real* p) -> real { if constexpr (WSM) return *p; else return __ldg(p); };
     auto dot = [&](int j, int kb, int ke, real (&acc)[TS]) {
 #pragma unroll
@@ -146,7 +159,7 @@ __device__ __forceinline__ void matvec(const real* __restrict__ W, int N, int K,
         int k = kb;
         // eight weight loads in flight per thread before their FMAs: a weight element is used by ONE thread (TS FMAs), so the
         // loop is bound by how many bytes the SM keeps in flight towards L2, not by the FMA pipe
-        for (; k + 8 <= ke; k += 8) {
+        for (; deep && k + 8 <= ke; k += 8) {
             real w8[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) w8[u] = ldw(wp + (size_t)(k + u) * N);
@@ -204,13 +217,84 @@ __device__ __forceinline__ void matvec(const real* __restrict__ W, int N, int K,
     }
 }
 
+// The m-wide contractions (N = m outputs, N even): a thread owns TWO adjacent outputs over HALF of the K range — one 8-byte
+// (fp64: 16-byte) weight load and one broadcast row load feed 2 TS FMAs, i.e. half the shared-memory traffic per FMA of matvec()
+// (the ncu capture of the first build showed the row loads, not the FMA pipe, as the limiter: short-scoreboard / MIO stalls).
+// The upper K-half's partial sums go through `part` ([N][TS]); the lower half's threads finish and run the epilogue of both
+// outputs.  Every thread of the CTA must call (block barriers inside).
+template <typename real, int TS, bool WSM, class Epi>
+__device__ __forceinline__ void matvec2(const real* __restrict__ W, int N, int K, const real* in, real* part, int tid, int NT,
+                                        Epi epi) {
+    const int G = NT >> 1, sl = tid / G, pp = tid % G, NP = N >> 1;
+    const int kb = sl ? (K >> 1) : 0, ke = sl ? K : (K >> 1);
+    auto ld2 = [](const real* p, real& x, real& y) {
+        if constexpr (sizeof(real) == 4) {
+            float2 t;
+            if constexpr (WSM) t = *reinterpret_cast<const float2*>(p); else t = __ldg(reinterpret_cast<const float2*>(p));
+            x = t.x; y = t.y;
+        } else {
+            double2 t;
+            if constexpr (WSM) t = *reinterpret_cast<const double2*>(p); else t = __ldg(reinterpret_cast<const double2*>(p));
+            x = t.x; y = t.y;
+        }
+    };
+    for (int p0 = 0; p0 < NP; p0 += G) {
+        const int p = p0 + pp;
+        real acc0[TS], acc1[TS];
+#pragma unroll
+        for (int s = 0; s < TS; ++s) { acc0[s] = real(0); acc1[s] = real(0); }
+        if (p < NP) {
+            const real* wp = W + 2 * p;
+            int k = kb;
+            for (; k + 4 <= ke; k += 4) {
+                real wx[4], wy[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) ld2(wp + (size_t)(k + u) * N, wx[u], wy[u]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    real a[TS];
+                    ld_row<real, TS>(in + (k + u) * TS, a);
+#pragma unroll
+                    for (int s = 0; s < TS; ++s) { acc0[s] = r_fma(wx[u], a[s], acc0[s]); acc1[s] = r_fma(wy[u], a[s], acc1[s]); }
+                }
+            }
+            for (; k < ke; ++k) {
+                real wx, wy, a[TS];
+                ld2(wp + (size_t)k * N, wx, wy);
+                ld_row<real, TS>(in + k * TS, a);
+#pragma unroll
+                for (int s = 0; s < TS; ++s) { acc0[s] = r_fma(wx, a[s], acc0[s]); acc1[s] = r_fma(wy, a[s], acc1[s]); }
+            }
+            if (sl == 1) {
+#pragma unroll
+                for (int s = 0; s < TS; ++s) { part[(2 * p) * TS + s] = acc0[s]; part[(2 * p + 1) * TS + s] = acc1[s]; }
+            }
+        }
+        __syncthreads();
+        if (sl == 0 && p < NP) {
+            real b0[TS], b1[TS];
+            ld_row<real, TS>(part + (2 * p) * TS, b0);
+            ld_row<real, TS>(part + (2 * p + 1) * TS, b1);
+#pragma unroll
+            for (int s = 0; s < TS; ++s) { acc0[s] += b0[s]; acc1[s] += b1[s]; }
+            epi(2 * p, acc0);
+            epi(2 * p + 1, acc1);
+        }
+        if (p0 + G < NP) __syncthreads();
+    }
+}
+
 template <typename real, int TS, bool WSM>
 __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<real> A) {
     extern __shared__ __align__(16) unsigned char grad_smem[];
     real* sm = reinterpret_cast<real*>(grad_smem);
     const int tid = threadIdx.x, NT = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = NT >> 5;
+    // the problem descriptor goes to shared memory: terrain_agent() takes it by reference and is not always inlined, and the address
+    // of a kernel parameter would force a local-memory copy of the whole argument struct (an L2 round trip per access)
+    __shared__ ProbPack s_prob;
+    if (tid == 0) s_prob = A.prob;
     const GradPack<real>& P = A.phi;
-    const ProbPack& pr = A.prob;
+    const ProbPack& pr = s_prob;
     const int d = P.d, D = P.D, m = P.m;
     const int smp = tid % TS, part_id = tid / TS, nparts = NT / TS;        // problem phase: NT / TS threads share a sample
     real* s = sm + A.o_s;     real* g = sm + A.o_g;     real* gb = sm + A.o_gb;   real* qv = sm + A.o_q;
@@ -230,7 +314,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
     __syncthreads();
 
     // per-sample sum over the threads that share a sample (fixed shuffle tree, then warps in fixed order); ends with a barrier
-    auto sample_sum = [&](real v) -> real {
+    auto sample_sum = [&](real v) __attribute__((always_inline)) -> real {
 #pragma unroll
         for (int off = TS; off < 32; off <<= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
         __syncthreads();
@@ -241,37 +325,45 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
         return t;
     };
 
+    // an m-wide contraction.  Weights from L2 (the wide nets): two outputs per thread over half of K each (measured on swarm50:
+    // 34.6 -> 32.9 ms per training iteration).  Weights staged in shared memory (m <= 128): one output per thread — the extra
+    // barrier and partial-sum round trip of matvec2 cost more than the saved row loads (singlequad 3.5 -> 4.0 ms).
+    auto mwide = [&](const real* Wm, int N, int K, const real* in, auto epi) __attribute__((always_inline)) {
+        if constexpr (WSM) matvec<real, TS, WSM>(Wm, N, K, in, part, 1, tid, NT, A.deep != 0, epi);
+        else matvec2<real, TS, WSM>(Wm, N, K, in, part, tid, NT, epi);
+    };
+
     // ---- grad Phi at the stage input in `s` -> g (and q = A'A s); terminal: X2 = u1 = u0 + h act(a1)
-    auto primal = [&](bool terminal) {
-        matvec<real, TS, WSM>(wb + P.off_W1t, m, D, s, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+    auto primal = [&](bool terminal) __attribute__((always_inline)) {
+        mwide(wb + P.off_W1t, m, D, s, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real b = Wb0[j];
 #pragma unroll
-            for (int q = 0; q < TS; ++q) { real av, tv; act_tanh(acc[q] + b, av, tv); u0[j * TS + q] = av; T0[j * TS + q] = tv; }
+            for (int q = 0; q < TS; ++q) { real av, tv; act_tanh_sel(A.precise != 0, acc[q] + b, av, tv); u0[j * TS + q] = av; T0[j * TS + q] = tv; }
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_Kft, m, m, u0, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        mwide(wb + P.off_Kft, m, m, u0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real b = Wb1[j], wv = Ww[j];
 #pragma unroll
             for (int q = 0; q < TS; ++q) {
                 real tv;
-                if (terminal) { real av; act_tanh(acc[q] + b, av, tv); X2[j * TS + q] = u0[j * TS + q] + h * av; }
+                if (terminal || A.precise) { real av; act_tanh_sel(A.precise != 0, acc[q] + b, av, tv); if (terminal) X2[j * TS + q] = u0[j * TS + q] + h * av; }
                 else tv = tanh_only(acc[q] + b);
                 T1[j * TS + q] = tv;
                 X1[j * TS + q] = tv * wv;                           // y
             }
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_Kr, m, m, X1, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        mwide(wb + P.off_Kr, m, m, X1, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real wv = Ww[j];
 #pragma unroll
             for (int q = 0; q < TS; ++q) { real z = wv + h * acc[q]; z1[j * TS + q] = z; OD[j * TS + q] = T0[j * TS + q] * z; }   // v
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_sym, D, D, s, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        matvec<real, TS, WSM>(wb + P.off_sym, D, D, s, part, 1, tid, NT, A.deep != 0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < TS; ++q) qv[j * TS + q] = acc[q];
         });
-        matvec<real, TS, WSM>(wb + P.off_W4, D, m, OD, part, A.nsplitD, tid, NT, [&](int j, real (&acc)[TS]) {
+        matvec<real, TS, WSM>(wb + P.off_W4, D, m, OD, part, A.nsplitD, tid, NT, A.deep != 0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real c = Wcw[j];
 #pragma unroll
             for (int q = 0; q < TS; ++q) g[j * TS + q] = (qv[j * TS + q] + acc[q]) + c;
@@ -281,7 +373,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
 
     // ---- calcLHQW at x = s[:d], p = g[:d]  ->  sc = (L, |Phi_t - H|, Q, W), qx (quadcopter rates);
     //      adjoint: also gb = d psi / d g and xd = direct d psi / d x for psi = ab.(-grad_p H) + cL L + cH |g_t - H|
-    auto problem = [&](bool adjoint, real cL, real cH) {
+    auto problem = [&](bool adjoint, real cL, real cH) __attribute__((always_inline)) {
         const real vmask = vm[smp];
         cL *= vmask; cH *= vmask;
         if (pr.kind == 2) {                              // Quadcopter.py:65-113, one agent
@@ -397,13 +489,13 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
 
     // ---- second-order sweep: tangent of the net along gb, its reverse, parameter gradients; sbar -> sb.
     //      terminal: bt[.] = beta (the adjoint of Phi itself), X2 = u1.
-    auto second_order = [&](bool terminal) {
-        matvec<real, TS, WSM>(wb + P.off_W1t, m, D, gb, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+    auto second_order = [&](bool terminal) __attribute__((always_inline)) {
+        mwide(wb + P.off_W1t, m, D, gb, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < TS; ++q) { OD[j * TS + q] = acc[q]; X1[j * TS + q] = T0[j * TS + q] * acc[q]; }     // odot, udot
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_Kft, m, m, X1, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        mwide(wb + P.off_Kft, m, m, X1, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real wv = Ww[j];
             real wsum = real(0), bsum = real(0);
 #pragma unroll
@@ -419,7 +511,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
             red_add(A.grad + P.g_b1 + j, bsum);
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_Kr, m, m, AD, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        mwide(wb + P.off_Kr, m, m, AD, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real wv = Ww[j];
             real bsum = real(0);
 #pragma unroll
@@ -434,11 +526,11 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
             red_add(A.grad + P.g_b0 + j, bsum);
         });
         __syncthreads();
-        matvec<real, TS, WSM>(wb + P.off_sym, D, D, gb, part, 1, tid, NT, [&](int j, real (&acc)[TS]) {
+        matvec<real, TS, WSM>(wb + P.off_sym, D, D, gb, part, 1, tid, NT, A.deep != 0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
 #pragma unroll
             for (int q = 0; q < TS; ++q) sb[j * TS + q] = acc[q];
         });
-        matvec<real, TS, WSM>(wb + P.off_W4, D, m, X2, part, A.nsplitD, tid, NT, [&](int j, real (&acc)[TS]) {
+        matvec<real, TS, WSM>(wb + P.off_W4, D, m, X2, part, A.nsplitD, tid, NT, A.deep != 0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real c = Wcw[j];
             real csum = real(0);
 #pragma unroll
@@ -461,7 +553,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
         }
         __syncthreads();
         // dK1[j][k] += h w_j sum_s T1[j][s] udot[k][s] + sum_s bar_a1[j][s] u0[k][s]
-        if (sizeof(real) == 4 && (m & 3) == 0 && (NT % (m / 4) == 0 || NT < m / 4)) {
+        if (A.use_v4 && sizeof(real) == 4 && (m & 3) == 0 && (NT % (m / 4) == 0 || NT < m / 4)) {
             // fp32: a thread owns FOUR consecutive columns k (its udot / u0 rows in registers) for a slice of the rows j; one
             // 16-byte vector reduction per row (REDG.ADD.F32x4, coalesced over the column groups) and 64 FMAs per pair of row loads
             const int KG = m >> 2, nrg = (NT >= KG) ? NT / KG : 1;
@@ -547,7 +639,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
         __syncthreads();
     };
 
-    auto rate = [&](int row, int si) -> real {         // dx/dt = -grad_p H
+    auto rate = [&](int row, int si) __attribute__((always_inline)) -> real {         // dx/dt = -grad_p H
         if (pr.kind != 2) return -g[row * TS + si];
         if (row < 6) return s[(6 + row) * TS + si];
         if (row < 9) { real gg = -qx[si] * qx[(1 + row - 6) * TS + si]; if (row == 8) gg = gg + real(pr.grav); return -gg; }
@@ -702,7 +794,7 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     P.g_K1 = gtake(m * m); P.g_b1 = gtake(m); P.g_len = go;
 
     const int NT = std::min(512, std::max(32, align_up(std::max(m, D), 32)));
-    if (m > 2048) return fail(NOC_ERR_UNSUPPORTED, "noc_ocflow_grad: m = %d > 2048", m);
+    if (m > 2048 || (m & 1)) return fail(NOC_ERR_UNSUPPORTED, "noc_ocflow_grad: m = %d (even widths up to 2048)", m);
     auto plan = [&](int TS, size_t& vec_bytes, bool& wsm) -> size_t {
         int so = 0;
         auto stake = [&](int cnt) { int o = so; so += align_up(cnt, 8); return o; };
@@ -711,7 +803,7 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
         A.o_z0 = stake((d + 4) * TS); A.o_za = stake((d + 4) * TS); A.o_sc = stake(SC_ROWS * TS); A.o_red = stake(32 * TS);
         A.o_qx = stake(4 * TS); A.o_as = stake(r * TS); A.o_ag = stake(r * TS); A.o_bt = stake(TS); A.o_vm = stake(TS);
         A.nsplitD = std::max(1, std::min(4, NT / align_up(D, 32)));
-        A.o_part = stake(A.nsplitD > 1 ? A.nsplitD * D * TS : 8);
+        A.o_part = stake(std::max(A.nsplitD > 1 ? A.nsplitD * D * TS : 8, m * TS));
         A.o_T0 = stake(m * TS); A.o_u0 = stake(m * TS); A.o_T1 = stake(m * TS); A.o_z1 = stake(m * TS);
         A.o_od = stake(m * TS); A.o_ad = stake(m * TS); A.o_x1 = stake(m * TS); A.o_x2 = stake(m * TS);
         A.o_w = so;
@@ -719,17 +811,22 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
         wsm = vec_bytes + (size_t)P.blob_len * sizeof(real) <= (size_t)smem_limit;
         return vec_bytes + (wsm ? (size_t)P.blob_len * sizeof(real) : 0);
     };
-    // tile width: 8 samples (measured: swarm50, n = 1024: 38 ms with 128 tiles of 8, 58 ms with 256 tiles of 4 — a wider tile
-    // amortises every weight load over more samples); 4 when the panels of 8 do not fit or fewer than half the SMs would get a tile
+    // tile width (measured, `bench.py --train`): wide nets want 8 samples per tile — every weight load is amortised over more
+    // samples (swarm50, n = 1024: 35 ms with 128 tiles of 8, 50 ms with 256 tiles of 4; singlequad 3.5 vs 5.6 ms); the narrow nets
+    // run one or two warps per CTA and want more CTAs instead (softcorridor, n = 1024: 1.5 ms with tiles of 4, 1.9 ms with 8)
     int TS = 8;
     size_t vec_bytes = 0;
     bool wsm = false;
     size_t smem = plan(TS, vec_bytes, wsm);
-    if (vec_bytes > (size_t)smem_limit || (n + 7) / 8 < (long long)(sm_count() / 2)) { TS = 4; smem = plan(TS, vec_bytes, wsm); }
+    const bool fits8 = vec_bytes <= (size_t)smem_limit;
+    if (!fits8 || (NT <= 64 && (n + 7) / 8 < 4LL * sm_count())) { TS = 4; smem = plan(TS, vec_bytes, wsm); }
     if (const char* e = getenv("NOC_GRAD_TS")) { int t = atoi(e); if (t == 4 || t == 8) { TS = t; smem = plan(TS, vec_bytes, wsm); } }
     if (vec_bytes > (size_t)smem_limit)
         return fail(NOC_ERR_NOMEM, "noc_ocflow_grad: panels of d=%d, m=%d need %zu B of shared memory (> %d)", d, m, vec_bytes, smem_limit);
     A.ntiles = (int)((n + TS - 1) / TS);
+    if (getenv("NOC_DEBUG"))
+        fprintf(stderr, "[noc] grad kernel: n=%lld d=%d m=%d TS=%d NT=%d tiles=%d smem=%zu (panels %zu, weights %s) limit=%d\n", n, d, m, TS, NT,
+                A.ntiles, smem, vec_bytes, wsm ? "staged" : "L2", smem_limit);
 
     real* blob = nullptr; real* xsave = nullptr; double* partials = nullptr;
     NOC_CUDA(cudaMallocAsync((void**)&blob, sizeof(real) * (size_t)P.blob_len, st));
@@ -746,6 +843,10 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.times = dtimes;
     A.alph0 = (real)alph[0]; A.alph3 = (real)alph[3]; A.alph4 = (real)alph[4]; A.alph5 = (real)alph[5];
     A.t_end = (real)t_end;
+    A.use_v4 = wsm ? 0 : 1; A.deep = 1;
+    if (const char* e = getenv("NOC_GRAD_PRECISE")) A.precise = atoi(e);
+    if (const char* e = getenv("NOC_GRAD_V4")) A.use_v4 = atoi(e);
+    if (const char* e = getenv("NOC_GRAD_DEEP")) A.deep = atoi(e);
     A.partials = partials; A.grad = gacc; A.grad_x = grad_x; A.xsave = xsave;
     void (*kern)(const GradArgs<real>) = nullptr;
     if (TS == 8) kern = wsm ? rollout_grad_kernel<real, 8, true> : rollout_grad_kernel<real, 8, false>;
