@@ -63,7 +63,6 @@ struct GradArgs {
     real* grad_x;              // [n][d] or NULL
     real* xsave;               // [ntiles][nt][4][d][TS]
     int nsplitD;               // K-slices of the D-wide contractions (K0'v, K0'bar_o)
-    int precise;               // experiment switch: libm activation pair
     int use_v4, deep;          // experiment switches: vector reductions for dK1, eight weight loads in flight
     // shared-memory offsets (elements)
     int o_s, o_g, o_gb, o_q, o_sb, o_xd, o_lam, o_xbn, o_xsum, o_z0, o_za, o_sc, o_red, o_qx, o_as, o_ag, o_bt, o_vm, o_part;
@@ -116,14 +115,27 @@ __device__ __forceinline__ void ld_row(const real* p, real (&v)[TS]) {
     }
 }
 
-// libm variants of the activation pair (experiment switch NOC_GRAD_PRECISE=1; the default is the MUFU pair of noc_rollout.cuh)
+// tanh near saturation.  The adjoint needs BOTH tanh(a) and 1 - tanh(a)^2, and most hidden units of the trained nets are deep in
+// saturation (|a| = 5 ... 40), where 1 - T*T from a rounded T keeps no significant digit (T within an ulp of 1 leaves
+// 1 - T^2 = 4e-7 with an absolute error of 1e-7).  The panels therefore keep the signed  q = e / (1 + e),  e = exp(-2|a|):
+//     tanh(a) = sign(a) (1 - 2q)        1 - tanh(a)^2 = 4 q (1 - q)        (q in [0, 1/2]: no cancellation in either)
+// and are rewritten with tanh itself once the derivative has been consumed (the parameter-gradient loops read tanh).
 template <typename real>
-__device__ __forceinline__ void act_tanh_sel(bool precise, real pre, real& av, real& tv) {
-    if (!precise) { act_tanh(pre, av, tv); return; }
+__device__ __forceinline__ void act_q(real pre, real& av, real& qs) {      // antiderivative of tanh (Phi.py:8-9) and signed q
     const real a = r_abs(pre);
-    if constexpr (sizeof(real) == 4) { const float e = expf(-2.f * a); av = a + log1pf(e); tv = copysignf((1.f - e) / (1.f + e), pre); }
-    else { const double e = exp(-2.0 * a); av = a + log1p(e); tv = copysign((1.0 - e) / (1.0 + e), pre); }
+    const real e = r_exp(real(-2) * a);
+    av = a + r_log1pe(e);
+    qs = copysign(r_div(e, real(1) + e), pre);
 }
+template <typename real>
+__device__ __forceinline__ real q_only(real pre) {
+    const real e = r_exp(real(-2) * r_abs(pre));
+    return copysign(r_div(e, real(1) + e), pre);
+}
+template <typename real>
+__device__ __forceinline__ real q_tanh(real qs) { return copysign(r_fma(real(-2), r_abs(qs), real(1)), qs); }
+template <typename real>
+__device__ __forceinline__ real q_dtanh(real qs) { const real q = r_abs(qs); return real(4) * q * (real(1) - q); }
 
 template <typename real>
 __device__ __forceinline__ real sgn(real v) { return real((v > real(0)) - (v < real(0))); }
@@ -338,25 +350,25 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
         mwide(wb + P.off_W1t, m, D, s, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real b = Wb0[j];
 #pragma unroll
-            for (int q = 0; q < TS; ++q) { real av, tv; act_tanh_sel(A.precise != 0, acc[q] + b, av, tv); u0[j * TS + q] = av; T0[j * TS + q] = tv; }
+            for (int q = 0; q < TS; ++q) { real av, qs; act_q(acc[q] + b, av, qs); u0[j * TS + q] = av; T0[j * TS + q] = qs; }   // T0: q-form
         });
         __syncthreads();
         mwide(wb + P.off_Kft, m, m, u0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real b = Wb1[j], wv = Ww[j];
 #pragma unroll
             for (int q = 0; q < TS; ++q) {
-                real tv;
-                if (terminal || A.precise) { real av; act_tanh_sel(A.precise != 0, acc[q] + b, av, tv); if (terminal) X2[j * TS + q] = u0[j * TS + q] + h * av; }
-                else tv = tanh_only(acc[q] + b);
-                T1[j * TS + q] = tv;
-                X1[j * TS + q] = tv * wv;                           // y
+                real qs;
+                if (terminal) { real av; act_q(acc[q] + b, av, qs); X2[j * TS + q] = u0[j * TS + q] + h * av; }
+                else qs = q_only(acc[q] + b);
+                T1[j * TS + q] = qs;                                // q-form
+                X1[j * TS + q] = q_tanh(qs) * wv;                   // y
             }
         });
         __syncthreads();
         mwide(wb + P.off_Kr, m, m, X1, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
             const real wv = Ww[j];
 #pragma unroll
-            for (int q = 0; q < TS; ++q) { real z = wv + h * acc[q]; z1[j * TS + q] = z; OD[j * TS + q] = T0[j * TS + q] * z; }   // v
+            for (int q = 0; q < TS; ++q) { real z = wv + h * acc[q]; z1[j * TS + q] = z; OD[j * TS + q] = q_tanh(T0[j * TS + q]) * z; }   // v
         });
         __syncthreads();
         matvec<real, TS, WSM>(wb + P.off_sym, D, D, s, part, 1, tid, NT, A.deep != 0, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
@@ -492,7 +504,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
     auto second_order = [&](bool terminal) __attribute__((always_inline)) {
         mwide(wb + P.off_W1t, m, D, gb, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
 #pragma unroll
-            for (int q = 0; q < TS; ++q) { OD[j * TS + q] = acc[q]; X1[j * TS + q] = T0[j * TS + q] * acc[q]; }     // odot, udot
+            for (int q = 0; q < TS; ++q) { OD[j * TS + q] = acc[q]; X1[j * TS + q] = q_tanh(T0[j * TS + q]) * acc[q]; }     // odot, udot
         });
         __syncthreads();
         mwide(wb + P.off_Kft, m, m, X1, [&](int j, real (&acc)[TS]) __attribute__((always_inline)) {
@@ -500,9 +512,10 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
             real wsum = real(0), bsum = real(0);
 #pragma unroll
             for (int q = 0; q < TS; ++q) {
-                const real ad = acc[q], t1 = T1[j * TS + q];
+                const real ad = acc[q], q1 = T1[j * TS + q], t1 = q_tanh(q1);
+                T1[j * TS + q] = t1;                                // from here on (dK1) the panel holds tanh itself
                 real ws = X1[j * TS + q] + h * t1 * ad;
-                real ba = h * wv * ad * (real(1) - t1 * t1);
+                real ba = h * wv * ad * q_dtanh(q1);
                 if (terminal) { const real b = bt[q]; ws += b * X2[j * TS + q]; ba += b * h * t1 * wv; }
                 AD[j * TS + q] = ba;
                 wsum += ws; bsum += ba;
@@ -518,8 +531,9 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
             for (int q = 0; q < TS; ++q) {
                 real bu = acc[q];
                 if (terminal) bu += bt[q] * wv;
-                const real t0 = T0[j * TS + q];
-                const real bo = (real(1) - t0 * t0) * OD[j * TS + q] * z1[j * TS + q] + t0 * bu;
+                const real q0 = T0[j * TS + q], t0 = q_tanh(q0);
+                T0[j * TS + q] = t0;                                // from here on (dK0) the panel holds tanh itself
+                const real bo = q_dtanh(q0) * OD[j * TS + q] * z1[j * TS + q] + t0 * bu;
                 X2[j * TS + q] = bo;
                 bsum += bo;
             }
@@ -844,7 +858,6 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     A.alph0 = (real)alph[0]; A.alph3 = (real)alph[3]; A.alph4 = (real)alph[4]; A.alph5 = (real)alph[5];
     A.t_end = (real)t_end;
     A.use_v4 = wsm ? 0 : 1; A.deep = 1;
-    if (const char* e = getenv("NOC_GRAD_PRECISE")) A.precise = atoi(e);
     if (const char* e = getenv("NOC_GRAD_V4")) A.use_v4 = atoi(e);
     if (const char* e = getenv("NOC_GRAD_DEEP")) A.deep = atoi(e);
     A.partials = partials; A.grad = gacc; A.grad_x = grad_x; A.xsave = xsave;

@@ -15,6 +15,10 @@ for name in (sys.argv[1:] or ["swarm50", "swap12", "singlequad", "softcorridor",
     prob.train()
     P, D, xi, _ = oracle_setup(name, torch.float64)
     D = dataclasses.replace(D, training=True)
+    if os.environ.get("NOC_ACC_NOQW"):                                   # network-only: no terrain / interaction terms
+        prob.alph_Q = prob.alph_W = 0.0
+        D = dataclasses.replace(D, alph_Q=0.0, alph_W=0.0)
+    print("alph", meta["alph"], "alph_Q/W", prob.alph_Q, prob.alph_W)
     for kind in ("adversarial", "plain"):
         n, nt = (6, 3) if name == "swarm50" else (13, 5)
         if kind == "adversarial":
