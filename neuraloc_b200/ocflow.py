@@ -177,20 +177,21 @@ class _RolloutWithAdjoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, Phi, prob, tspan, nt, alph, *params):
         sums, grad, gx = ocflow_grad_sums(x, Phi, prob, tspan, nt, alph, want_xgrad=x.requires_grad)
-        cnt = sums[7]
-        means = (sums[:7] / cnt).to(x.dtype)
+        means = (sums[:7] / sums[7]).to(x.dtype)
         Jc = means[0] + alph[0] * means[1] + alph[3] * means[2] + alph[4] * means[3] + alph[5] * means[4]
-        inv = (1.0 / cnt).to(x.dtype)
-        ctx.pgrads = [(g * inv).to(device=p.device, dtype=p.dtype) for g, p in zip(split_param_grads(Phi, grad), params)]
+        inv = (1.0 / sums[7]).to(x.dtype)
+        ctx.flat = grad * inv                      # ONE scaling of the flat gradient; the per-parameter tensors are views of it
+        ctx.Phi = Phi
         ctx.gx = None if gx is None else (gx * inv).to(x.device)
-        ctx.needs = [p.requires_grad for p in params]
+        ctx.like = [(p.device, p.dtype, p.requires_grad) for p in params]
         Jc, means = Jc.to(x.device), means.to(x.device)
         ctx.mark_non_differentiable(means)
         return Jc, means
 
     @staticmethod
     def backward(ctx, gJ, _gmeans):
-        pg = [(g * gJ.to(g.device)) if need else None for g, need in zip(ctx.pgrads, ctx.needs)]
+        flat = ctx.flat * gJ.to(ctx.flat.device)
+        pg = [g.to(device=dev, dtype=dt) if need else None for g, (dev, dt, need) in zip(split_param_grads(ctx.Phi, flat), ctx.like)]
         gx = None if ctx.gx is None else ctx.gx * gJ.to(ctx.gx.device)
         return (gx, None, None, None, None, None, *pg)
 
