@@ -366,8 +366,14 @@ def test_input_is_not_mutated_and_errors_are_loud(nb):
         a = mean_vec(nb.OCflow(xt, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"]))
         b = mean_vec(nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"]))
     assert torch.equal(x, keep) and np.array_equal(a, b)
-    with pytest.raises(RuntimeError):        # autograd on, parameters require grad
-        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
+    # autograd on, parameters require grad: the default mode is the training path (differentiable Jc, tests/test_gpu_grad.py) and
+    # returns the same objective; the modes without an adjoint raise instead of returning something non-differentiable
+    Jg, _ = nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
+    assert Jg.requires_grad and abs(float(Jg) - b[0]) <= 2e-5 * abs(b[0])
+    with pytest.raises(RuntimeError):
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"], noMean=True)
+    with pytest.raises(RuntimeError):
+        nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"], intermediates=True)
     with torch.no_grad(), pytest.raises(ValueError):
         nb.OCflow(x[:, :3], net, prob, [0.0, 1.0], 4, "rk4", meta["alph"])
     with torch.no_grad(), pytest.raises(ValueError):
