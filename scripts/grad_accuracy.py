@@ -25,6 +25,8 @@ for name in (sys.argv[1:] or ["swarm50", "swap12", "singlequad", "softcorridor",
             x = adversarial_batch(name, D, xi, meta["var0"], n)
         else:
             n = 64 if name == "swarm50" else 256
+            if os.environ.get("NOC_ACC_NT"):                         # the reference's training nt: the rollout the net was trained for
+                nt, n = int(os.environ["NOC_ACC_NT"]), min(n, 32)
             g = torch.Generator().manual_seed(5)
             x = xi + meta["var0"] * torch.randn(n, xi.shape[1], generator=g, dtype=torch.float64)
             if name == "singlequad":
@@ -45,6 +47,18 @@ for name in (sys.argv[1:] or ["swarm50", "swap12", "singlequad", "softcorridor",
             rms = lambda a, b: float(((a.double().cpu().reshape(b.shape) - b) ** 2).mean().sqrt() / (b ** 2).mean().sqrt())
             al = meta["alph"]
             Jk = float(sums[0] + al[0] * sums[1] + al[3] * sums[2] + al[4] * sums[3] + al[5] * sums[4])
+            with torch.no_grad():
+                from oracle import ocflow_oracle as orc
+                c64 = [float(c.sum()) for c in orc.ocflow(x, P, D, [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)[1]]
+                c32 = [float(c.double().sum()) for c in orc.ocflow(x.float(), P.to(torch.float32), D.to(torch.float32), [0.0, 1.0], nt, "rk4", meta["alph"], noMean=True)[1]]
+                zk, _ = nb.OCflow(x.float().cuda(), net, prob, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+                z64, _ = orc.ocflow(x, P, D, [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+                z32, _ = orc.ocflow(x.float(), P.to(torch.float32), D.to(torch.float32), [0.0, 1.0], nt, "rk4", meta["alph"], intermediates=True)
+            dd = x.shape[1]
+            serr = lambda z: float(((z.double().cpu()[:, :dd, -1] - z64[:, :dd, -1]).norm(dim=1) / z64[:, :dd, -1].norm(dim=1)).max())
+            print("      cost sums rel err [L G HJt HJfin HJgrad]: grad kernel %s | torch fp32 %s | final-state err: forward kernel %.1e torch fp32 %.1e" % (
+                " ".join("%.1e" % (abs(float(sums[i]) - c64[i]) / max(abs(c64[i]), 1e-300)) for i in range(5)),
+                " ".join("%.1e" % (abs(c32[i] - c64[i]) / max(abs(c64[i]), 1e-300)) for i in range(5)), serr(zk), serr(z32)))
             print("      grad_x max %.1e (torch %.1e) rms %.1e (torch %.1e) | K1 rms %.1e (torch %.1e) | J rel %.1e (torch %.1e)" % (
                 rel(gx, X64), rel(X32, X64), rms(gx, X64), rms(X32, X64), rms(got["K1"], G64["K1"]), rms(G32["K1"], G64["K1"]),
                 abs(Jk - float(J64)) / abs(float(J64)), abs(float(J32) - float(J64)) / abs(float(J64))))

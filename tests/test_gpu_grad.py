@@ -38,7 +38,9 @@ def _compare(name, dtype, training, n, nt, monkeypatch=None, ts=None):
     Jsum = float(sums[0] + al[0] * sums[1] + al[3] * sums[2] + al[4] * sums[3] + al[5] * sums[4])
     # fp32: the gradient is compared with the fp64 gradient, so the tolerance is fp32's own conditioning on these batches —
     # torch's fp32 autograd is 1e-5 ... 7e-4 away from the fp64 gradient on them (scripts/grad_accuracy.py prints both distances);
-    # the kernel measures 2e-6 ... 9e-4, except on swarm50 where it is 3e-3 ... 5e-3 (open item)
+    # the kernel measures 2e-6 ... 9e-4, except on swarm50's SHORT rollouts (nt = 3 with a net trained for nt = 26: fp32 loses 1e-5
+    # of the state, kernel and torch alike, and the gradient amplifies it to 3e-3 ... 5e-3) — gated at the training
+    # length in test_grad_fp32_swarm50_at_training_nt
     tolJ, tolg = (1e-10, 1e-8) if dtype == torch.float64 else (2e-5, 1.5e-2 if name == "swarm50" else 5e-3)
     assert abs(Jsum - float(Ja)) <= tolJ * abs(float(Ja)), (Jsum, float(Ja))
     assert abs(Jsum - float(Jn.double().sum())) <= tolJ * abs(float(Ja))            # same objective as the forward-only kernels
@@ -66,6 +68,24 @@ def test_grad_fp64_matches_autograd(name, training):
 def test_grad_fp32_matches_autograd(name):
     n, nt = (6, 3) if name == "swarm50" else (13, 5)
     _compare(name, torch.float32, True, n, nt)
+
+
+def test_grad_fp32_swarm50_at_training_nt():
+    """swarm50 at the reference's training length (README.md:118: nt = 26), a plain batch from rho_0: the fp32 gradient within 2e-4
+    of the fp64 autograd gradient (measured 8e-6 ... 3.5e-5; torch's own fp32 autograd: 6e-6 ... 2.6e-5)."""
+    import neuraloc_b200 as nb
+    net, prob, P, D, xi64, meta = _setup("swarm50", torch.float32, True)
+    g = torch.Generator().manual_seed(5)
+    n, nt = 12, 26
+    x64 = xi64 + meta["var0"] * torch.randn(n, 150, generator=g, dtype=torch.float64)
+    Ja, Ga, xa = autograd_of_oracle(x64, P, D, [0.0, 1.0], nt, meta["alph"])
+    sums, grad, gx = nb.ocflow_grad_sums(x64.float().cuda(), net, prob, [0.0, 1.0], nt, meta["alph"], want_xgrad=True)
+    got = dict(zip(ORDER, nb.split_param_grads(net, grad)))
+    for k in NAMES:
+        ref = Ga[k]
+        err = float((got[k].double().cpu().reshape(ref.shape) - ref).abs().max())
+        assert err <= 2e-4 * max(float(ref.abs().max()), 1e-30), (k, err / float(ref.abs().max()))
+    assert float((gx.double().cpu() - xa).abs().max()) <= 2e-4 * float(xa.abs().max())
 
 
 @pytest.mark.parametrize("ts", [4, 8])
