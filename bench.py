@@ -364,6 +364,9 @@ def train_mode(args, W, dtype, threads):
     # forward flops x (1 forward + 4 stages re-evaluated with 8 instead of 4 contractions + 4 rank-TS updates)
     d, m = x.shape[1], meta["m"]
     fl = flops_per_sample_step(d, m, 2, min(10, d + 1))
+    import ctypes
+    pk = ctypes.c_double(0.0)
+    nb._cabi.check(nb._cabi.lib().noc_measure_fma_peak(0 if W["dtype"] == "f32" else 1, ctypes.byref(pk)))
     line = {"metric": "train_sample_steps_per_sec", "value": n * nt / t, "unit": "sample-steps/s (forward + backward)", "n_gpus": 1,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": statistics.mean(ms), "higher_is_better": True,
             "dtype": W["dtype"], "data": "synthetic",
@@ -372,7 +375,9 @@ def train_mode(args, W, dtype, threads):
                        "Jc": float(Jc), "grad_norm": gnorm},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "unit": "TFLOP/s",
-                         "achieved": 4.0 * fl * n * nt / t / 1e12,
+                         "achieved": 4.0 * fl * n * nt / t / 1e12, "peak": pk.value, "frac": 4.0 * fl * n * nt / t / 1e12 / pk.value,
+                         "kernel": "rollout_grad_kernel (FMA panels, one launch per iteration)",
+                         "peak_source": "measured live: register-resident FMA micro-benchmark on all SMs (noc_measure_fma_peak)",
                          "note": "algorithmic flops of forward + adjoint = 4 x the forward's (8 instead of 4 contractions per "
                                  "re-evaluated stage + the parameter-gradient outer products) / time; FMA kernel"}}
     if not args.no_cpu_baseline:
