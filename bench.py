@@ -372,7 +372,7 @@ def train_mode(args, W, dtype, threads):
             "dtype": W["dtype"], "data": "synthetic",
             "config": {"workload": "%s, one trainOC.py iteration (OCflow in train mode + Jc.backward()), n_train=%d, nt=%d "
                                    "(README.md:103-123), x ~ xInit + var0*N(0,I)" % (args.workload, n, nt),
-                       "Jc": float(Jc), "grad_norm": gnorm},
+                       "Jc": float(Jc.detach()), "grad_norm": gnorm},
             "gpu_launches": launches,
             "roofline": {"bound": "fp32_fma" if W["dtype"] == "f32" else "fp64_fma", "unit": "TFLOP/s",
                          "achieved": 4.0 * fl * n * nt / t / 1e12, "peak": pk.value, "frac": 4.0 * fl * n * nt / t / 1e12 / pk.value,
@@ -401,7 +401,7 @@ def train_mode(args, W, dtype, threads):
             best = min(best, time.perf_counter() - t0)
         gn = float(torch.sqrt(sum((t_.grad.double() ** 2).sum() for t_ in leaves)))
         line["cpu_baseline"] = {"value": n * nt / best, "unit": "sample-steps/s (forward + backward)", "cores": threads, "kind": "port",
-                                "ms_per_iteration": best * 1e3, "Jc": float(Jr), "grad_norm": gn,
+                                "ms_per_iteration": best * 1e3, "Jc": float(Jr.detach()), "grad_norm": gn,
                                 "sample": "the same batch (n=%d, nt=%d), torch autograd through the oracle port, best of 2" % (n, nt)}
     return line
 
