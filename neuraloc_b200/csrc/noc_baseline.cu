@@ -23,7 +23,7 @@ struct BaseArgs {
     real alphG;
     real* loss;         // [n]
     real* gradU;        // [n][nt][nc] or NULL
-    real* zsave;        // [n][nt][d]   (gradU only)
+    real* zsave;        // [warps of the grid][nt][d]: state history of the sample a warp is working on (gradU only)
 };
 
 template <typename real>
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(128) baseline_loss_kernel(const BaseArgs<real>
     const real cut = real(pr.cutW), c2 = real(2 * pr.r * pr.r), inv_r2 = real(1.0 / (pr.r * pr.r));
     for (long long smp = (long long)blockIdx.x * nwarp + warp; smp < A.n; smp += (long long)gridDim.x * nwarp) {
         const real* Us = A.U + smp * nt * nc;
-        real* zs = A.gradU ? A.zsave + smp * nt * d : nullptr;
+        real* zs = A.gradU ? A.zsave + ((size_t)blockIdx.x * nwarp + warp) * nt * d : nullptr;   // per warp, reused by its next sample
         for (int c = lane; c < d; c += 32) Z[c] = A.z0[smp * d + c];
         __syncwarp();
         real loss = real(0);
@@ -186,15 +186,15 @@ int baseline_loss(const ProbPack& pr, const real* U, const real* z0, long long n
     memset(&A, 0, sizeof A);
     A.prob = pr; A.U = U; A.z0 = z0; A.n = n; A.d = d; A.nt = nt; A.nc = (pr.kind == NOC_PROB_QUADCOPTER) ? 4 : d;
     A.alphG = (real)alphG; A.loss = loss; A.gradU = gradU;
-    real* zsave = nullptr;
-    if (gradU) {
-        NOC_CUDA(cudaMallocAsync((void**)&zsave, sizeof(real) * (size_t)n * nt * d, st));
-        A.zsave = zsave;
-    }
     const int warps = 4;
     const size_t smem = sizeof(real) * 2 * d * warps;
-    const int grid = (int)std::min<long long>((n + warps - 1) / warps, 32LL * sm_count());
-    baseline_loss_kernel<real><<<std::max(1, grid), 32 * warps, smem, st>>>(A);
+    const int grid = std::max(1, (int)std::min<long long>((n + warps - 1) / warps, 32LL * sm_count()));
+    real* zsave = nullptr;
+    if (gradU) {
+        NOC_CUDA(cudaMallocAsync((void**)&zsave, sizeof(real) * (size_t)grid * warps * nt * d, st));
+        A.zsave = zsave;
+    }
+    baseline_loss_kernel<real><<<grid, 32 * warps, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
     if (zsave) NOC_CUDA(cudaFreeAsync(zsave, st));

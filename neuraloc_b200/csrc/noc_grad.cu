@@ -8,8 +8,8 @@
 // Layout: a CTA owns a tile of TS samples for the whole forward + backward sweep.  Every vector of the network lives in shared
 // memory as a panel [unit][TS] (sample contiguous), thread j owns output unit j of every contraction (weights K-major so that
 // the lanes of a warp read consecutive addresses; staged in shared memory when the whole blob fits, else read through L1/L2),
-// with TS accumulators in registers.  The forward sweep stores the four stage inputs of every RK step ([tile][step][stage]
-// [d][TS], coalesced); the backward sweep re-evaluates grad Phi at each of them and applies the hand-derived adjoint
+// with TS accumulators in registers.  The forward sweep stores the four stage inputs of every RK step ([CTA][step][stage]
+// [d][TS], coalesced, reused by the CTA's next tile); the backward sweep re-evaluates grad Phi at each of them and applies the hand-derived adjoint
 // (tests/adjoint_ref.py restates the same formulas with torch ops and tests/test_adjoint_formulas.py checks them against
 // autograd of the oracle):
 //
@@ -61,7 +61,7 @@ struct GradArgs {
     double* partials;          // [ntiles][8] per-tile cost sums (+ count), summed by finish_costs_kernel
     real* grad;                // [g_len] sums over the samples (atomic adds)
     real* grad_x;              // [n][d] or NULL
-    real* xsave;               // [ntiles][nt][4][d][TS]
+    real* xsave;               // [grid][nt][4][d][TS]: stage inputs of the tile a CTA is working on (L2-sized: <= 74 MB for swarm50)
     int nsplitD;               // K-slices of the D-wide contractions (K0'v, K0'bar_o)
     int use_v4, deep;          // experiment switches: vector reductions for dK1, eight weight loads in flight
     // shared-memory offsets (elements)
@@ -664,7 +664,7 @@ __global__ void __launch_bounds__(512, 1) rollout_grad_kernel(const GradArgs<rea
     const int nZ = (d + 4) * TS, nX = d * TS;
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const long long base = (long long)tile * TS;
-        real* xs_tile = A.xsave + (size_t)tile * A.nt * 4 * nX;
+        real* xs_tile = A.xsave + (size_t)blockIdx.x * A.nt * 4 * nX;   // per CTA: a tile's forward + backward finish before the next tile starts
         if (tid < TS) vm[tid] = (base + tid < A.n) ? real(1) : real(0);
         for (int i = tid; i < nZ; i += NT) {
             const int r = i / TS, si = i % TS;
@@ -849,7 +849,6 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     pack_phi_grad_kernel<real><<<pgrid, 256, 0, st>>>(raw, P, blob);
     count_launch();
     P.blob = blob;
-    NOC_CUDA(cudaMallocAsync((void**)&xsave, sizeof(real) * (size_t)A.ntiles * nt * 4 * d * TS, st));
     NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)A.ntiles, st));
     real* gacc = nullptr;
     NOC_CUDA(cudaMallocAsync((void**)&gacc, sizeof(real) * (size_t)P.g_len, st));
@@ -869,6 +868,8 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return fail(NOC_ERR_NOMEM, "noc_ocflow_grad: kernel does not fit on an SM (%zu B shared memory)", smem);
     const int grid = std::max(1, std::min(A.ntiles, per_sm * sm_count()));
+    NOC_CUDA(cudaMallocAsync((void**)&xsave, sizeof(real) * (size_t)grid * nt * 4 * d * TS, st));
+    A.xsave = xsave;
     kern<<<grid, NT, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
