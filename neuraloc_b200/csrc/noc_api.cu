@@ -794,15 +794,11 @@ static int ocflow_grad_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
     std::vector<double> tab((size_t)nt * 5);
     if (stage_times) memcpy(tab.data(), stage_times, sizeof(double) * tab.size());
     else stage_times_host(t0, t1, nt, tab.data());
-    double* dtab = nullptr;
-    NOC_CUDA(cudaMallocAsync((void**)&dtab, sizeof(double) * tab.size(), st));
-    NOC_CUDA(cudaMemcpyAsync(dtab, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
-    rc = grad_rollout<real>(ph->d, ph->m, ph->r, (double)P.h, R, pr, (const real*)x, n, dtab, nt, alph, t1, (double*)out_costs,
-                            (real*)grad, (real*)grad_x, g_smem_optin, st);
-    cudaError_t e = cudaFreeAsync(dtab, st);
-    if (rc) return rc;
-    if (e != cudaSuccess) return fail(NOC_ERR_CUDA, "cudaFreeAsync failed: %s", cudaGetErrorString(e));
-    return NOC_OK;
+    ScratchBuf b_tab;                                      // freed (stream-ordered) on every exit path
+    NOC_CUDA(b_tab.alloc(sizeof(double) * tab.size(), st));
+    NOC_CUDA(cudaMemcpyAsync(b_tab.p, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice, st));
+    return grad_rollout<real>(ph->d, ph->m, ph->r, (double)P.h, R, pr, (const real*)x, n, b_tab.as<double>(), nt, alph, t1,
+                              (double*)out_costs, (real*)grad, (real*)grad_x, g_smem_optin, st);
 }
 
 template <typename real>

@@ -189,15 +189,14 @@ int baseline_loss(const ProbPack& pr, const real* U, const real* z0, long long n
     const int warps = 4;
     const size_t smem = sizeof(real) * 2 * d * warps;
     const int grid = std::max(1, (int)std::min<long long>((n + warps - 1) / warps, 32LL * sm_count()));
-    real* zsave = nullptr;
+    ScratchBuf b_zsave;                                    // freed (stream-ordered) on every exit path
     if (gradU) {
-        NOC_CUDA(cudaMallocAsync((void**)&zsave, sizeof(real) * (size_t)grid * warps * nt * d, st));
-        A.zsave = zsave;
+        NOC_CUDA(b_zsave.alloc(sizeof(real) * (size_t)grid * warps * nt * d, st));
+        A.zsave = b_zsave.as<real>();
     }
     baseline_loss_kernel<real><<<grid, 32 * warps, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
-    if (zsave) NOC_CUDA(cudaFreeAsync(zsave, st));
     return NOC_OK;
 }
 

@@ -842,16 +842,17 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
         fprintf(stderr, "[noc] grad kernel: n=%lld d=%d m=%d TS=%d NT=%d tiles=%d smem=%zu (panels %zu, weights %s) limit=%d\n", n, d, m, TS, NT,
                 A.ntiles, smem, vec_bytes, wsm ? "staged" : "L2", smem_limit);
 
-    real* blob = nullptr; real* xsave = nullptr; double* partials = nullptr;
-    NOC_CUDA(cudaMallocAsync((void**)&blob, sizeof(real) * (size_t)P.blob_len, st));
+    ScratchBuf b_blob, b_xsave, b_partials, b_gacc;       // freed (stream-ordered) on every exit path
+    NOC_CUDA(b_blob.alloc(sizeof(real) * (size_t)P.blob_len, st));
+    real* blob = b_blob.as<real>();
     NOC_CUDA(cudaMemsetAsync(blob, 0, sizeof(real) * (size_t)P.blob_len, st));
     int pgrid = std::min(std::max(1, ceil_div(std::max(m * m, m * D), 256)), 4 * sm_count());
     pack_phi_grad_kernel<real><<<pgrid, 256, 0, st>>>(raw, P, blob);
     count_launch();
     P.blob = blob;
-    NOC_CUDA(cudaMallocAsync((void**)&partials, sizeof(double) * 8 * (size_t)A.ntiles, st));
-    real* gacc = nullptr;
-    NOC_CUDA(cudaMallocAsync((void**)&gacc, sizeof(real) * (size_t)P.g_len, st));
+    NOC_CUDA(b_partials.alloc(sizeof(double) * 8 * (size_t)A.ntiles, st));
+    NOC_CUDA(b_gacc.alloc(sizeof(real) * (size_t)P.g_len, st));
+    real* gacc = b_gacc.as<real>();
     NOC_CUDA(cudaMemsetAsync(gacc, 0, sizeof(real) * (size_t)P.g_len, st));
     A.prob = pr; A.x = x; A.n = n; A.nt = nt; A.times = dtimes;
     A.alph0 = (real)alph[0]; A.alph3 = (real)alph[3]; A.alph4 = (real)alph[4]; A.alph5 = (real)alph[5];
@@ -859,7 +860,7 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     A.use_v4 = wsm ? 0 : 1; A.deep = 1;
     if (const char* e = getenv("NOC_GRAD_V4")) A.use_v4 = atoi(e);
     if (const char* e = getenv("NOC_GRAD_DEEP")) A.deep = atoi(e);
-    A.partials = partials; A.grad = gacc; A.grad_x = grad_x; A.xsave = xsave;
+    A.partials = b_partials.as<double>(); A.grad = gacc; A.grad_x = grad_x;
     void (*kern)(const GradArgs<real>) = nullptr;
     if (TS == 8) kern = wsm ? rollout_grad_kernel<real, 8, true> : rollout_grad_kernel<real, 8, false>;
     else kern = wsm ? rollout_grad_kernel<real, 4, true> : rollout_grad_kernel<real, 4, false>;
@@ -868,21 +869,15 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
     if (per_sm < 1) return fail(NOC_ERR_NOMEM, "noc_ocflow_grad: kernel does not fit on an SM (%zu B shared memory)", smem);
     const int grid = std::max(1, std::min(A.ntiles, per_sm * sm_count()));
-    NOC_CUDA(cudaMallocAsync((void**)&xsave, sizeof(real) * (size_t)grid * nt * 4 * d * TS, st));
-    A.xsave = xsave;
+    NOC_CUDA(b_xsave.alloc(sizeof(real) * (size_t)grid * nt * 4 * d * TS, st));
+    A.xsave = b_xsave.as<real>();
     kern<<<grid, NT, smem, st>>>(A);
     count_launch();
     NOC_CUDA(cudaGetLastError());
     unpack_grad_kernel<real><<<std::min(std::max(1, ceil_div(P.g_len, 256)), 4 * sm_count()), 256, 0, st>>>(gacc, grad, GS);
     count_launch();
     NOC_CUDA(cudaGetLastError());
-    int frc = launch_finish(partials, A.ntiles, out_sums, st);
-    if (frc) return frc;
-    NOC_CUDA(cudaFreeAsync(gacc, st));
-    NOC_CUDA(cudaFreeAsync(partials, st));
-    NOC_CUDA(cudaFreeAsync(xsave, st));
-    NOC_CUDA(cudaFreeAsync(blob, st));
-    return NOC_OK;
+    return launch_finish(A.partials, A.ntiles, out_sums, st);
 }
 
 template int grad_rollout<float>(int, int, int, double, const PhiRaw<float>&, const ProbPack&, const float*, long long, const double*, int,

@@ -22,6 +22,18 @@ int launch_finish(const double* partials, int nblocks, double* out, cudaStream_t
             return fail(NOC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
     } while (0)
 
+// stream-ordered scratch that is returned to the pool on every exit path (error returns included)
+struct ScratchBuf {
+    void* p = nullptr;
+    cudaStream_t st = nullptr;
+    ScratchBuf() = default;
+    ScratchBuf(const ScratchBuf&) = delete;
+    ScratchBuf& operator=(const ScratchBuf&) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) { st = s; return cudaMallocAsync(&p, bytes ? bytes : 1, s); }
+    template <typename T> T* as() const { return static_cast<T*>(p); }
+    ~ScratchBuf() { if (p) cudaFreeAsync(p, st); }
+};
+
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int align_up(int a, int b) { return ceil_div(a, b) * b; }
 
