@@ -134,3 +134,46 @@ def test_grad_modes_that_are_not_differentiable_raise():
         nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk4", meta["alph"], noMean=True)
     with pytest.raises(RuntimeError):
         nb.OCflow(x, net, prob, [0.0, 1.0], 4, "rk1", meta["alph"])
+
+
+def test_short_training_run_matches_cpu_autograd():
+    """trainOC.py:169-174 for 25 iterations from the same random initialisation, fp64: Adam on the GPU with the fused
+    forward + adjoint kernel, and Adam on the CPU with autograd through the oracle rollout — the two loss histories and the final
+    weights must coincide (the reference's training loop, transplanted)."""
+    import copy
+    import neuraloc_b200 as nb
+    from oracle import ocflow_oracle as orc
+    _, meta0 = __import__("helpers").load_ckpt("softcorridor")
+    alph = meta0["alph"]
+    torch.manual_seed(3)
+    net_gpu = nb.Phi(nTh=2, m=32, d=4, alph=alph).double()
+    net_cpu = copy.deepcopy(net_gpu)
+    net_gpu = net_gpu.cuda()
+    prob, _, _, xinit = nb.initProb("softcorridor", 2, 2, var0=1.0, alph=alph, cvt=lambda v: v.double().cuda())
+    prob.train()
+    D, xi = orc.make_problem("softcorridor", alph, torch.float64)
+    D = dataclasses.replace(D, training=True)
+    g = torch.Generator().manual_seed(9)
+    x = xi + torch.randn(256, 4, generator=g, dtype=torch.float64)
+    nt, iters = 8, 25
+    hist = {}
+    for tag, net, run in (("gpu", net_gpu, None), ("cpu", net_cpu, None)):
+        optim = torch.optim.Adam(net.parameters(), lr=0.01)
+        losses = []
+        for _ in range(iters):
+            optim.zero_grad()
+            if tag == "gpu":
+                Jc, cs = nb.OCflow(x.cuda(), net, prob, tspan=[0.0, 1.0], nt=nt, stepper="rk4", alph=alph)
+            else:
+                Pg = orc.PhiParams(net.A, net.c.weight, net.c.bias, net.w.weight, [l.weight for l in net.N.layers],
+                                   [l.bias for l in net.N.layers], net.N.h)
+                Jc, cs = orc.ocflow(x, Pg, D, [0.0, 1.0], nt, "rk4", alph)
+            Jc.backward()
+            optim.step()
+            losses.append(float(Jc.detach()))
+        hist[tag] = losses
+    a, b = np.array(hist["gpu"]), np.array(hist["cpu"])
+    assert b[-1] < b[0]                                                   # it trains
+    assert np.abs(a - b).max() <= 1e-7 * np.abs(b).max(), (a, b)
+    for pg, pc in zip(net_gpu.parameters(), net_cpu.parameters()):
+        assert float((pg.detach().cpu() - pc.detach()).abs().max()) <= 1e-7 * max(float(pc.detach().abs().max()), 1e-30)
