@@ -109,6 +109,71 @@ def test_dropin_hook_runs_an_evalOC_style_script(nb, tmp_path):
     assert abs(vals[8] - 3.95163178) < 1e-4 and abs(vals[9] - 5.23088646) < 1e-3
 
 
+def test_dropin_hook_runs_a_trainOC_style_script(nb, tmp_path):
+    """trainOC.py:150-210 through the hook without the reference checkout: Adam iterations with `Jc.backward()`, validation under
+    no_grad in eval mode, resampling, and the `{args, state_dict}` checkpoint it saves (trainOC.py:204-207) reloaded evalOC-style."""
+    src = tmp_path / "src"
+    src.mkdir()
+    (src / "__init__.py").write_text("")
+    (src / "OCflow.py").write_text(textwrap.dedent("""
+        def OCflow(*a, **k):
+            raise AssertionError("the stand-in reference OCflow ran: the drop-in hook did not rebind it")
+        stepRK4 = stepRK1 = ocOdefun = OCflow
+    """))
+    script = tmp_path / "train_like.py"
+    script.write_text(textwrap.dedent("""
+        import sys, json, argparse, os, torch
+        sys.path.insert(0, %r)
+        from src.OCflow import OCflow                 # what trainOC.py:13 does
+        import neuraloc_b200 as nb
+        args = argparse.Namespace(data="softcorridor", m=32, nTh=2, nt=10, nt_val=16, n_train=512, var0=1.0, lr=0.01,
+                                  alph=[100.0, 10000.0, 300.0, 0.02, 0.02, 0.02], niters=30, val_freq=10, sample_freq=15)
+        device = torch.device("cuda:0")
+        cvt = lambda x: x.type(torch.float32).to(device, non_blocking=True)
+        torch.manual_seed(0)
+        prob, x0, x0v, xInit = nb.initProb(args.data, args.n_train, 256, var0=args.var0, alph=args.alph, cvt=cvt)
+        net = nb.Phi(nTh=args.nTh, m=args.m, d=x0.size(1), alph=args.alph).to(torch.float32).to(device)
+        optim = torch.optim.Adam(net.parameters(), lr=args.lr)
+        net.train(); prob.train()
+        hist, val = [], []
+        best = float("inf")
+        for itr in range(1, args.niters + 1):
+            optim.zero_grad()
+            Jc, cs = OCflow(x0, net, prob, tspan=[0.0, 1.0], nt=args.nt, stepper="rk4", alph=net.alph)
+            Jc.backward()
+            optim.step()
+            hist.append(float(Jc.detach()))
+            line = '{:05d} {:9.3e}  {:8.2e}  {:8.2e}'.format(itr, Jc, cs[0], cs[1])      # the reference formats the tensors directly
+            if itr %% args.val_freq == 0:
+                with torch.no_grad():
+                    net.eval(); prob.eval()
+                    tl, tcs = OCflow(x0v, net, prob, tspan=[0.0, 1.0], nt=args.nt_val, stepper="rk4", alph=net.alph)
+                    val.append(float(tl))
+                    if tl.item() < best:
+                        best = tl.item()
+                        torch.save({"args": args, "state_dict": net.state_dict()}, "ckpt.pth")
+                    net.train(); prob.train()
+            if itr %% args.sample_freq == 0:
+                x0 = nb.resample(x0, xInit, args.var0, cvt)
+        ck = torch.load("ckpt.pth", map_location=lambda storage, loc: storage, weights_only=False)
+        net2 = nb.Phi(nTh=ck["args"].nTh, m=ck["args"].m, d=4, alph=ck["args"].alph)
+        net2.load_state_dict(ck["state_dict"])
+        with torch.no_grad():
+            prob.eval()
+            J2, _ = OCflow(x0v.cpu(), net2, prob, tspan=[0.0, 1.0], nt=args.nt_val, stepper="rk4", alph=net2.alph)
+        print("RESULT " + json.dumps({"hist": hist, "val": val, "best": best, "reloaded": float(J2)}))
+    """ % os.path.join(ROOT, "tests")))
+    env = dict(os.environ, PYTHONPATH=os.pathsep.join([os.path.join(ROOT, "neuraloc_b200", "dropin"), ROOT, str(tmp_path)]))
+    for k in ("NOC_FORCE_PATH", "NOC_NO_LAT"):
+        env.pop(k, None)
+    out = subprocess.run([sys.executable, str(script)], env=env, capture_output=True, text=True, cwd=str(tmp_path), timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    r = json.loads([l for l in out.stdout.splitlines() if l.startswith("RESULT ")][0][7:])
+    assert len(r["hist"]) == 30 and len(r["val"]) == 3 and all(np.isfinite(r["hist"]))
+    assert r["hist"][-1] < 0.6 * r["hist"][0]                         # the loss goes down
+    assert abs(r["reloaded"] - r["best"]) <= 1e-3 * abs(r["best"])    # the saved checkpoint reproduces its validation loss (CPU tensors: host entry)
+
+
 @pytest.mark.parametrize("name", ["softcorridor", "swarm50"])
 def test_real_pth_checkpoint_evalOC_and_timeOC_flow(nb, tmp_path, name):
     """A real checkpoint FILE in the reference's layout — torch.save({'args': argparse.Namespace, 'state_dict': ...}) as
