@@ -100,7 +100,10 @@ __global__ void pack_phi_grad_kernel(const PhiRaw<real> R, const GradPack<real> 
 // one panel row (TS consecutive samples) <-> registers, as 16-byte vectors
 template <typename real, int TS>
 __device__ __forceinline__ void ld_row(const real* p, real (&v)[TS]) {
-    if constexpr (sizeof(real) == 4) {
+    if constexpr (TS * sizeof(real) < 16) {                 // tiles of one or two samples (narrow nets): scalar row loads
+#pragma unroll
+        for (int i = 0; i < TS; ++i) v[i] = p[i];
+    } else if constexpr (sizeof(real) == 4) {
 #pragma unroll
         for (int i = 0; i < TS / 4; ++i) {
             float4 t = reinterpret_cast<const float4*>(p)[i];
@@ -834,7 +837,11 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     size_t smem = plan(TS, vec_bytes, wsm);
     const bool fits8 = vec_bytes <= (size_t)smem_limit;
     if (!fits8 || (NT <= 64 && (n + 7) / 8 < 4LL * sm_count())) { TS = 4; smem = plan(TS, vec_bytes, wsm); }
-    if (const char* e = getenv("NOC_GRAD_TS")) { int t = atoi(e); if (t == 4 || t == 8) { TS = t; smem = plan(TS, vec_bytes, wsm); } }
+    // ... and tiles of 2 while even tiles of 4 leave the GPU short of warps (measured at the README batch sizes: swap12 2.43 -> 1.99 ms,
+    // swap2 1.55 -> 1.41, softcorridor 1.77 -> 1.71; tiles of 1 are slower again: 3.9 / 1.8 / 2.5 ms)
+    if (TS == 4 && m <= 64 && wsm && (n + 3) / 4 < 8LL * sm_count()) { TS = 2; smem = plan(TS, vec_bytes, wsm); }
+    if (const char* e = getenv("NOC_GRAD_TS")) { int t = atoi(e); if (t == 2 || t == 4 || t == 8) { TS = t; smem = plan(TS, vec_bytes, wsm); } }
+    if (TS < 4 && !wsm) return fail(NOC_ERR_UNSUPPORTED, "noc_ocflow_grad: tiles of %d samples are built for staged weights only", TS);
     if (vec_bytes > (size_t)smem_limit)
         return fail(NOC_ERR_NOMEM, "noc_ocflow_grad: panels of d=%d, m=%d need %zu B of shared memory (> %d)", d, m, vec_bytes, smem_limit);
     A.ntiles = (int)((n + TS - 1) / TS);
@@ -863,7 +870,8 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     A.partials = b_partials.as<double>(); A.grad = gacc; A.grad_x = grad_x;
     void (*kern)(const GradArgs<real>) = nullptr;
     if (TS == 8) kern = wsm ? rollout_grad_kernel<real, 8, true> : rollout_grad_kernel<real, 8, false>;
-    else kern = wsm ? rollout_grad_kernel<real, 4, true> : rollout_grad_kernel<real, 4, false>;
+    else if (TS == 4) kern = wsm ? rollout_grad_kernel<real, 4, true> : rollout_grad_kernel<real, 4, false>;
+    else kern = rollout_grad_kernel<real, 2, true>;
     NOC_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
     NOC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, NT, smem));
@@ -880,9 +888,14 @@ int grad_rollout(int d, int m, int r, double h, const PhiRaw<real>& raw, const P
     return launch_finish(A.partials, A.ntiles, out_sums, st);
 }
 
+// one object per precision (Makefile: -DNOC_GRAD_ONLY=32 / 64) so that the two sets of instantiations compile in parallel
+#if !defined(NOC_GRAD_ONLY) || NOC_GRAD_ONLY == 32
 template int grad_rollout<float>(int, int, int, double, const PhiRaw<float>&, const ProbPack&, const float*, long long, const double*, int,
                                  const double*, double, double*, float*, float*, int, cudaStream_t);
+#endif
+#if !defined(NOC_GRAD_ONLY) || NOC_GRAD_ONLY == 64
 template int grad_rollout<double>(int, int, int, double, const PhiRaw<double>&, const ProbPack&, const double*, long long, const double*, int,
                                   const double*, double, double*, double*, double*, int, cudaStream_t);
+#endif
 
 }  // namespace noc

@@ -88,10 +88,10 @@ def test_grad_fp32_swarm50_at_training_nt():
     assert float((gx.double().cpu() - xa).abs().max()) <= 2e-4 * float(xa.abs().max())
 
 
-@pytest.mark.parametrize("ts", [4, 8])
-@pytest.mark.parametrize("name", ["swap12", "singlequad", "swarm50"])
+@pytest.mark.parametrize("name,ts", [("swap12", 2), ("swap12", 4), ("swap12", 8), ("softcorridor", 2), ("swap2", 2), ("singlequad", 4),
+                                     ("singlequad", 8), ("swarm50", 4), ("swarm50", 8)])
 def test_grad_tile_widths(name, ts, monkeypatch):
-    """both tile widths, more tiles than one CTA wave for the narrow nets, a ragged last tile"""
+    """every tile width (2: staged-weight nets only), more tiles than one CTA wave for the narrow nets, a ragged last tile"""
     n, nt = (21, 2) if name == "swarm50" else (301, 4)
     fits64 = not (name == "swarm50" and ts == 8)          # 8-sample fp64 panels of the m = 512 net exceed shared memory
     _compare(name, torch.float64 if fits64 else torch.float32, True, n, nt, monkeypatch, ts)
