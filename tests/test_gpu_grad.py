@@ -28,7 +28,7 @@ def _compare(name, dtype, training, n, nt, monkeypatch=None, ts=None):
     if ts is not None:
         monkeypatch.setenv("NOC_GRAD_TS", str(ts))
     net, prob, P, D, xi64, meta = _setup(name, dtype, training)
-    x64 = adversarial_batch(name, D, xi64, meta["var0"], n)
+    x64 = adversarial_batch(name, D, xi64, meta["var0"], max(n, 4))[:n].contiguous()      # the builder edits rows 0..3
     Ja, Ga, xa = autograd_of_oracle(x64, P, D, [0.0, 1.0], nt, meta["alph"])
     sums, grad, gx = nb.ocflow_grad_sums(x64.to(dtype).cuda(), net, prob, [0.0, 1.0], nt, meta["alph"], want_xgrad=True)
     with torch.no_grad():
@@ -62,6 +62,12 @@ def _compare(name, dtype, training, n, nt, monkeypatch=None, ts=None):
 def test_grad_fp64_matches_autograd(name, training):
     n, nt = (6, 3) if name == "swarm50" else (13, 5)
     _compare(name, torch.float64, training, n, nt)
+
+
+@pytest.mark.parametrize("name", ["softcorridor", "singlequad", "swarm50"])
+def test_grad_single_sample(name):
+    """n = 1 (one valid row in its tile, the rest padding), as a one-state fine-tuning step would call it"""
+    _compare(name, torch.float64, True, 1, 3)
 
 
 @pytest.mark.parametrize("name", PROBLEMS)
