@@ -26,8 +26,9 @@
  *   - scratch is allocated stream-ordered (cudaMallocAsync) from the device's default memory pool; on first use of a device
  *     the library raises that pool's release threshold to 1 GiB (env NOC_POOL_KEEP_MB overrides) so that freed scratch is
  *     reused instead of being returned to the driver at every synchronisation — a process-wide setting of that device's pool;
- *     noc_ocflow_host grows it further to the size of its own device buffers (at most 1/8 of the device's memory) so that
- *     repeated calls on multi-GB host batches do not pay the driver for the buffers every time
+ *     the large per-call buffers (noc_ocflow_host's device copies of x and of the outputs, the intermediates staging buffers)
+ *     come from a second, library-owned pool per device whose threshold follows the largest call (at most 1/8 of the device's
+ *     memory, or NOC_POOL_KEEP_MB), so that repeated calls on multi-GB host batches do not pay the driver for them every time
  *   - there is no CPU implementation behind any of these: without a CUDA device they fail with
  *     NOC_ERR_CUDA
  */

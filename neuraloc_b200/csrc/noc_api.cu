@@ -342,21 +342,46 @@ int device_facts() {
     return NOC_OK;
 }
 
-// A host-entry call whose device buffers exceed the pool's release threshold pays the driver for them on EVERY call (measured on
-// swarm50, 2^22 samples = 2.5 GB of input: 6.2-6.7 s per call instead of 6.0 s).  Grow the threshold to cover the call, bounded by
-// 1/8 of the device's memory (NOC_POOL_KEEP_MB, when set, is the user's explicit choice and is left alone).
-void pool_keep_at_least(size_t bytes) {
-    if (getenv("NOC_POOL_KEEP_MB")) return;
+// Large per-call buffers (the host entry point's device copies of x and of the outputs, the intermediates staging buffers) come
+// from a pool of their own, one per device, whose release threshold follows the largest call (bounded by 1/8 of the device's
+// memory; NOC_POOL_KEEP_MB, when set, is the bound instead).  In the default pool they were either above the 1 GiB threshold —
+// a 2^22-sample swarm50 call (2.5 GB of input) paid the driver for its buffers on EVERY call, 6.2-6.7 s instead of 6.0 s — or cut
+// up by the small scratch allocations of the calls in between, so that every few calls a 200 MB buffer had to be mapped afresh
+// (sporadic +70 ms on singlequad's 0.37 s calls).
+static cudaMemPool_t g_big_pool[64] = {nullptr};
+static bool g_big_pool_failed[64] = {false};
+int big_reserve(size_t bytes) {
     int dev = 0;
-    cudaMemPool_t pool;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetDefaultMemPool(&pool, dev) != cudaSuccess) return;
-    size_t free_b = 0, total_b = 0;
-    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return;
-    unsigned long long want = (unsigned long long)bytes + (256ull << 20), cap = (unsigned long long)total_b / 8, cur = 0;
-    if (want > cap) want = cap;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return (int)cudaErrorInvalidDevice;
     std::lock_guard<std::mutex> lock(g_facts_mu);
+    if (!g_big_pool[dev] && !g_big_pool_failed[dev]) {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&g_big_pool[dev], &props) != cudaSuccess) { (void)cudaGetLastError(); g_big_pool[dev] = nullptr; g_big_pool_failed[dev] = true; }
+    }
+    cudaMemPool_t pool = g_big_pool[dev];
+    if (!pool) return (int)cudaSuccess;                    // fall back to the default pool (big_alloc)
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return (int)cudaSuccess;
+    unsigned long long cap = (unsigned long long)total_b / 8, want = (unsigned long long)bytes + (64ull << 20), cur = 0;
+    if (const char* e = getenv("NOC_POOL_KEEP_MB")) cap = (unsigned long long)atoll(e) << 20;
+    if (want > cap) want = cap;
     if (cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &cur) == cudaSuccess && cur < want)
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &want);
+    return (int)cudaSuccess;
+}
+int big_alloc(void** p, size_t bytes, cudaStream_t st) {
+    int dev = 0;
+    cudaMemPool_t pool = nullptr;
+    if (cudaGetDevice(&dev) == cudaSuccess && dev >= 0 && dev < 64) {
+        std::lock_guard<std::mutex> lock(g_facts_mu);
+        pool = g_big_pool[dev];
+    }
+    return (int)(pool ? cudaMallocFromPoolAsync(p, bytes ? bytes : 1, pool, st) : cudaMallocAsync(p, bytes ? bytes : 1, st));
 }
 
 // candidate configurations in order of preference for (dtype, m); NOC_FORCE_CFG=<id> pins one (tests)
@@ -710,7 +735,7 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
     }
     const long long rows_per = (((n + nchunk - 1) / nchunk + 127) / 128) * 128;
     if (mode == NOC_MODE_MEAN) ob = sizeof(double) * 8 * (size_t)nchunk;
-    if (device_facts() == NOC_OK) pool_keep_at_least(xb + ob + zb + cb);
+    big_reserve(xb + ob + zb + cb);
     void *xd = nullptr, *od = nullptr, *zd = nullptr, *cd = nullptr;
     auto release = [&] {                                   // one cleanup path: every exit frees what was allocated
         if (xd) cudaFreeAsync(xd, st);
@@ -720,10 +745,10 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
         xd = od = zd = cd = nullptr;
     };
     {
-        cudaError_t e = cudaMallocAsync(&xd, xb, st);
-        if (e == cudaSuccess && ob) e = cudaMallocAsync(&od, ob, st);
-        if (e == cudaSuccess && zb) e = cudaMallocAsync(&zd, zb, st);
-        if (e == cudaSuccess && cb) e = cudaMallocAsync(&cd, cb, st);
+        cudaError_t e = (cudaError_t)big_alloc(&xd, xb, st);
+        if (e == cudaSuccess && ob) e = (cudaError_t)big_alloc(&od, ob, st);
+        if (e == cudaSuccess && zb) e = (cudaError_t)big_alloc(&zd, zb, st);
+        if (e == cudaSuccess && cb) e = (cudaError_t)big_alloc(&cd, cb, st);
         if (e != cudaSuccess) {
             release();
             (void)cudaGetLastError();

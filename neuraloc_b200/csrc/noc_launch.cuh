@@ -14,7 +14,8 @@ int fail(int code, const char* fmt, ...);      // sets noc_last_error(), returns
 void count_launch();                            // kernel-launch counter                 (noc_api.cu)
 int sm_count();                                 // SMs of the current device             (noc_api.cu)
 int launch_finish(const double* partials, int nblocks, double* out, cudaStream_t st);   // (noc_api.cu)
-void pool_keep_at_least(size_t bytes);          // grow the pool's release threshold to cover a large per-call buffer (noc_api.cu)
+int big_reserve(size_t bytes);                  // large per-call buffers: their own per-device pool, threshold follows the call (noc_api.cu)
+int big_alloc(void** p, size_t bytes, cudaStream_t st);   // cudaError_t as int; freed with cudaFreeAsync
 
 #define NOC_CUDA(expr)                                                                               \
     do {                                                                                             \

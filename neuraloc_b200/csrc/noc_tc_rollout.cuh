@@ -801,8 +801,8 @@ int launch_tc(TcArgs A, int smem_limit, cudaStream_t st, double* out_sums) {
     float* stage = nullptr;
     if (A.mode == NOC_MODE_INTERMEDIATES) {
         const size_t bytes = sizeof(float) * (size_t)A.ntiles * (A.nt + 1) * (SH::NZ + SH::NCTRL) * 128;
-        pool_keep_at_least(bytes);                       // repeated intermediates calls reuse the staging buffer instead of paying the driver
-        if (cudaMallocAsync((void**)&stage, bytes, st) != cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
+        big_reserve(bytes);                              // repeated intermediates calls reuse the staging buffer instead of paying the driver
+        if (big_alloc((void**)&stage, bytes, st) != (int)cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
     }
     A.stage = stage;
     kern<<<grid, SH::NT, smem_req, st>>>(A);

@@ -1006,8 +1006,8 @@ int launch_ts(TsArgs A, const PhiRaw<float>& raw, int D, int r, int smem_limit, 
     float* stage = nullptr;
     if (A.mode == NOC_MODE_INTERMEDIATES && !getenv("NOC_TS_NOSTAGE")) {
         const size_t bytes = sizeof(float) * (size_t)A.ntiles * (A.nt + 1) * (SH::NZ + SH::d) * 128;
-        pool_keep_at_least(bytes);                       // repeated intermediates calls reuse the staging buffer instead of paying the driver
-        if (cudaMallocAsync((void**)&stage, bytes, st) != cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
+        big_reserve(bytes);                              // repeated intermediates calls reuse the staging buffer instead of paying the driver
+        if (big_alloc((void**)&stage, bytes, st) != (int)cudaSuccess) { stage = nullptr; (void)cudaGetLastError(); }
     }
     A.stage = stage;
     long long* trace = nullptr;

@@ -18,7 +18,7 @@ with torch.no_grad():
         nb.ocflow_sums(x, net, prob, [0.0, 1.0], NT, "rk4", meta["alph"]); nb.ocflow_sums(xh, net, prob, [0.0, 1.0], NT, "rk4", meta["alph"])
     torch.cuda.synchronize()
     td, th = [], []
-    for _ in range(4):
+    for _ in range(int(os.environ.get("NOC_PROBE_REPS", "4"))):
         t0 = time.perf_counter(); nb.ocflow_sums(x, net, prob, [0.0, 1.0], NT, "rk4", meta["alph"]); torch.cuda.synchronize(); td.append(time.perf_counter() - t0)
         t0 = time.perf_counter(); nb.ocflow_sums(xh, net, prob, [0.0, 1.0], NT, "rk4", meta["alph"]); torch.cuda.synchronize(); th.append(time.perf_counter() - t0)
 print("e2e_probe %s n=%d pool_keep=%s: device-resident %s s | host buffers %s s | ratio %.4f" % (
