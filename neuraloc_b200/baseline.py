@@ -10,6 +10,7 @@ differentiable with respect to the controls (`err.backward()`, baseline2D.py:97-
 import ctypes as C
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _cabi
 from .ocflow import _dtype_code, _prob_struct, _require_cuda
@@ -48,6 +49,7 @@ class _BaselineLoss(torch.autograd.Function):
         return loss.to(U.device)
 
     @staticmethod
+    @once_differentiable          # the kernels produce first derivatives only: a double backward raises instead of returning zeros
     def backward(ctx, gout):
         return (None if ctx.gU is None else ctx.gU * gout.reshape(-1, 1, 1), None, None, None)
 

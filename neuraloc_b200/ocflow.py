@@ -20,6 +20,7 @@ import ctypes as C
 import weakref
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _cabi
 
@@ -189,6 +190,7 @@ class _RolloutWithAdjoint(torch.autograd.Function):
         return Jc, means
 
     @staticmethod
+    @once_differentiable          # the kernels produce first derivatives only: a double backward raises instead of returning zeros
     def backward(ctx, gJ, _gmeans):
         flat = ctx.flat * gJ.to(ctx.flat.device)
         pg = [g.to(device=dev, dtype=dt) if need else None for g, (dev, dt, need) in zip(split_param_grads(ctx.Phi, flat), ctx.like)]
