@@ -131,7 +131,7 @@ int noc_ocflow(const noc_phi_t* phi, const noc_prob_t* prob, const void* x, int6
  * Copies x host->device, runs noc_ocflow on `stream`, copies the results back and synchronises `stream`.
  * Mean / noMean batches of >= 256 Ki rows are processed as up to 8 row chunks (multiples of 128 rows: per-sample results are
  * unchanged; mean-mode chunk sums are added on the host in chunk order) so that a chunk's copy overlaps the previous chunk's
- * rollout; the chunks use two short-lived internal streams ordered after / before `stream`.
+ * rollout; the chunks use two internal streams ordered after / before `stream` (created once per host thread and device, reused).
  * phi / prob tensors stay device pointers (uploaded once by the caller). */
 int noc_ocflow_host(const noc_phi_t* phi, const noc_prob_t* prob, const void* x_host, int64_t n,
                     const double* stage_times, double t0, double t1, int32_t nt, int32_t stepper,

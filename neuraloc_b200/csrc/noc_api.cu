@@ -766,8 +766,15 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
         // overlaps the next chunk's first wave instead of idling SMs
         cudaStream_t cs = nullptr, as = nullptr;
         cudaEvent_t ready = nullptr, joined = nullptr, copied[64] = {nullptr};
-        cudaError_t e = cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&as, cudaStreamNonBlocking);
+        // the two helper streams are created once per host thread and device and reused (creating and destroying them per call
+        // showed up as sporadic stalls of the calling thread)
+        static thread_local cudaStream_t t_cs[64] = {nullptr}, t_as[64] = {nullptr};
+        int dev = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e == cudaSuccess && (dev < 0 || dev >= 64)) e = cudaErrorInvalidDevice;
+        if (e == cudaSuccess && !t_cs[dev]) e = cudaStreamCreateWithFlags(&t_cs[dev], cudaStreamNonBlocking);
+        if (e == cudaSuccess && !t_as[dev]) e = cudaStreamCreateWithFlags(&t_as[dev], cudaStreamNonBlocking);
+        if (e == cudaSuccess) { cs = t_cs[dev]; as = t_as[dev]; }
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&joined, cudaEventDisableTiming);
         if (e == cudaSuccess) e = cudaEventRecord(ready, st);                 // xd / od exist (stream-ordered allocation on st)
@@ -795,8 +802,6 @@ static int ocflow_host_impl(const noc_phi_t* ph, const noc_prob_t* pb, const voi
         for (int c = 0; c < 64; ++c) if (copied[c]) cudaEventDestroy(copied[c]);
         if (ready) cudaEventDestroy(ready);
         if (joined) cudaEventDestroy(joined);
-        if (cs) cudaStreamDestroy(cs);
-        if (as) cudaStreamDestroy(as);
     }
     if (rc == NOC_OK) {
         cudaError_t e = cudaSuccess;
